@@ -1,0 +1,157 @@
+/*
+ * include/snesgpu.h -- C ABI of the B200-native palette-optimisation engine (libsnesgpu.so).
+ *
+ * The reference (aexoden/snesimage) has no FFI of its own: the hot path is the private
+ * `OptimizedImage` method set in /root/reference/src/lib.rs.  This header is the seam a maintainer
+ * would bind from Rust (`extern "C"` block): one entry point per
+ * `OptimizedImage` method, plus batched entry points for the candidate loops inside
+ * `optimize_palette_entry_{random,nes,channel}`.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative SNES_E_* code; snes_last_error() returns a
+ *     thread-local message (the Rust side wraps it as anyhow!(msg).context(..), mirroring the
+ *     `.context("Unable to optimize image")` strings of lib.rs:82,186,212,...).
+ *   - host pointers are borrowed for the duration of the call only; the library owns all device
+ *     memory.  Calls are synchronous unless the name ends in `_dev`.
+ *   - a snes_ctx (and the images created from it) is not thread-safe, like the reference.
+ *   - there is NO CPU fallback: every compute entry point fails with SNES_E_CUDA if no sm_100 GPU.
+ */
+#ifndef SNESGPU_H
+#define SNESGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNES_OK 0
+#define SNES_E_INVALID (-1)  /* bad argument (size, index, config) */
+#define SNES_E_CUDA (-2)     /* CUDA runtime error / no device */
+#define SNES_E_KMEANS (-3)   /* cogset's assert!(2 <= k && k < n) would panic */
+#define SNES_E_NOMEM (-4)
+
+#define SNES_WIDTH 256            /* lib.rs:29 */
+#define SNES_HEIGHT 256           /* lib.rs:30 */
+#define SNES_NES_COLOR_COUNT 56   /* lib.rs:31 */
+
+typedef struct snes_ctx snes_ctx;
+typedef struct snes_image snes_image; /* struct OptimizedImage, lib.rs:33-43 */
+
+/* config::Config, /root/reference/src/config.rs:13-30 (the fields OptimizedImage::new consumes) */
+typedef struct snes_config {
+    int32_t subpalette_count;     /* -c, default 1 */
+    int32_t subpalette_size;      /* -s, default 7 */
+    uint8_t dither;               /* -d */
+    uint8_t perceptual_palettes;  /* --perceptual-palettes */
+    uint8_t nes;                  /* --nes */
+    uint8_t reserved;
+} snes_config;
+
+/* (best error, candidate index) pair produced per image by the batched evaluators; 16 bytes so a
+ * step's results for all images form one all-gather payload. */
+typedef struct snes_best {
+    double err;
+    int32_t idx;  /* index into the candidate list, -1 if no candidate was evaluated */
+    int32_t pad;
+} snes_best;
+
+const char *snes_last_error(void);
+int snes_version(void);
+
+/* ---- context: one per GPU (one process per GPU) -------------------------------------------- */
+int snes_ctx_create(int device, snes_ctx **out);
+void snes_ctx_destroy(snes_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t snes_ctx_kernel_launches(const snes_ctx *ctx);
+/* make the library enqueue on an external CUDA stream (e.g. torch's current stream); NULL = own stream */
+int snes_ctx_set_stream(snes_ctx *ctx, void *cuda_stream);
+int snes_ctx_synchronize(snes_ctx *ctx);
+/* how many candidate evaluations have their intermediates live at once (default 16, env SNESGPU_CHUNK) */
+int snes_ctx_set_chunk(snes_ctx *ctx, int evaluations);
+
+/* ---- OptimizedImage ------------------------------------------------------------------------- */
+/* OptimizedImage::new (lib.rs:46-65).  rgba: width*height*4 bytes, r,g,b,a.  Only 256x256 is accepted
+ * (the reference's own tile table is fixed at 32x32, lib.rs:58,565).  Uploads the image and
+ * precomputes the source-side SSIMULACRA2 planes. */
+int snes_image_new(snes_ctx *ctx, const uint8_t *rgba, int width, int height, const snes_config *cfg, snes_image **out);
+void snes_image_free(snes_image *im);
+
+int snes_image_initialize_tiles(snes_image *im);     /* lib.rs:79-189 */
+int snes_image_recalculate_palettes(snes_image *im); /* lib.rs:407-415 */
+int snes_image_optimize(snes_image *im);             /* lib.rs:425-501 */
+int snes_image_error(snes_image *im, double *err);   /* lib.rs:503-548 */
+int snes_image_as_rgba(snes_image *im, uint8_t *out_rgba /* 65536*4 */); /* lib.rs:550-577 */
+/* lib.rs:579-625 + serde_json's compact to_string(): writes at most cap bytes (NUL-terminated when it
+ * fits) and always stores the required length (without NUL) in *len. */
+int snes_image_as_json(snes_image *im, char *buf, size_t cap, size_t *len);
+
+/* lib.rs:191-240; the 64 `rand::rng()` draws become the explicit list cand[ncand][3] (5-bit r,g,b) */
+int snes_image_optimize_palette_entry_random(snes_image *im, int palette, int index, const uint8_t *cand, int ncand);
+int snes_image_optimize_palette_entry_nes(snes_image *im, int palette, int index);                  /* lib.rs:242-284 */
+int snes_image_optimize_palette_entry_channel(snes_image *im, int palette, int index, int channel); /* lib.rs:286-328 */
+
+/* state accessors (fields of OptimizedImage / Palette) */
+int snes_image_get_palette(snes_image *im, uint8_t *out /* C*S*3 */);
+int snes_image_set_palette(snes_image *im, const uint8_t *in);
+int snes_image_get_tile_palettes(snes_image *im, uint8_t *out /* 1024 */);
+int snes_image_set_tile_palettes(snes_image *im, const uint8_t *in);
+int snes_image_get_palette_map(snes_image *im, uint8_t *out /* 65536 */);
+int snes_image_set_palette_map(snes_image *im, const uint8_t *in);
+
+/* ---- the same methods over a batch of images (independent OptimizedImages sharing one Config) -- */
+int snes_batch_initialize_tiles(snes_ctx *ctx, snes_image *const *images, int nimg);     /* lib.rs:79-189 */
+int snes_batch_recalculate_palettes(snes_ctx *ctx, snes_image *const *images, int nimg); /* lib.rs:407-415 */
+int snes_batch_optimize(snes_ctx *ctx, snes_image *const *images, int nimg);             /* lib.rs:425-501 */
+int snes_batch_error(snes_ctx *ctx, snes_image *const *images, int nimg, double *errors /* nimg, optional */);
+/* asynchronous error(): refreshes each image's cached error on the context's stream; d_errors optional */
+int snes_batch_error_dev(snes_ctx *ctx, snes_image *const *images, int nimg, double *d_errors);
+
+/* ---- batched candidate evaluation: the loops at lib.rs:205-220, 252-262, 296-306 ------------- */
+/* For every image j and candidate k: colours[palette*S+index] = cand[j][k]; optimize(); error().
+ * The images' own state is not modified.  scores[nimg*ncand], maps[nimg*ncand*65536] and best[nimg]
+ * are optional (NULL to skip).  best[j] is the strict-< first minimum over k (lib.rs:216). */
+int snes_batch_eval_candidates(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
+                               const uint8_t *cand /* nimg*ncand*3 */, int ncand, double *scores, uint8_t *maps,
+                               snes_best *best);
+/* Same with device-resident candidate list / outputs, asynchronous on the context's stream.
+ * cand_idx_base is added to every best[j].idx (a rank's offset into a sharded candidate list). */
+int snes_batch_eval_candidates_dev(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
+                                   const uint8_t *d_cand, int ncand, int cand_idx_base, double *d_scores,
+                                   snes_best *d_best);
+/* Accept rule of lib.rs:199,216-219,236-237 applied per image after the (possibly cross-rank) argmin:
+ * if best[j].err < current error of image j, entry (palette,index) becomes cand_all[j][best[j].idx] and
+ * the image is re-optimised; the image's cached error is updated.  d_cand_all holds ncand_all candidates
+ * per image (the full, unsharded list).  Asynchronous on the context's stream. */
+int snes_batch_apply_best_dev(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
+                              const uint8_t *d_cand_all, int ncand_all, const snes_best *d_best);
+/* Host-buffer convenience for one whole optimiser step over many images (eval + argmin + accept). */
+int snes_batch_step_random(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
+                           const uint8_t *cand /* nimg*ncand*3 */, int ncand, snes_best *best /* optional */,
+                           double *errors_after /* nimg, optional */);
+
+/* optimize_palette_entry_nes / _channel for every image of a batch (lib.rs:242-284, 286-328) */
+int snes_batch_step_nes(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index, snes_best *best,
+                        double *errors_after);
+int snes_batch_step_channel(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index, int channel,
+                            snes_best *best, double *errors_after);
+
+/* ---- colour primitives exposed for tests (lib.rs:628-795, 1080-1100) ------------------------- */
+/* Nearest entry for n targets (f64 triples) against a list of ncolors 5-bit colours on the GPU. */
+int snes_closest_color_index(snes_ctx *ctx, const uint8_t *colors5, int ncolors, const double *targets, int n,
+                             int cielab, int32_t *out_index);
+/* SnesColor::new_nes_only (lib.rs:640-660) for n colours. */
+int snes_new_nes_only(snes_ctx *ctx, const uint8_t *colors5, int n, int cielab, uint8_t *out5);
+/* Debug/test taps: positive-XYB pyramid and blurred source planes of an image, [scale][ch][y][x] f32,
+ * 87360*3 floats each. */
+int snes_image_debug_planes(snes_image *im, float *xyb, float *mu1, float *s11);
+/* per-pixel Lab<D65,f32> of the original (perceptual_palettes only), 65536*4 floats (L,a,b,0) */
+int snes_image_debug_lab(snes_image *im, float *lab);
+/* centres[256*3] and status[512] (status[p] per problem, status[C+p] = Lloyd iterations) of the last k-means */
+int snes_image_kmeans_debug(snes_image *im, double *centres, int32_t *status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

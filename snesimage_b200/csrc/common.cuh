@@ -1,0 +1,127 @@
+// Shared device-side definitions for libsnesgpu (sm_100a).
+//
+// Numerics contract: this translation unit is compiled with -fmad=false, so every f32/f64 operation
+// below is the IEEE operation as written; fused multiply-adds appear only where __fmaf_rn()/fma() is
+// spelled out (where ssimulacra2/yuvxyb use mul_add).  With the same operation order as the CPU
+// oracle, all f32 planes are bit-identical to it; only the order of the final f64 sums differs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace snes {
+
+constexpr int W = 256, H = 256;
+constexpr int NPIX = W * H;
+constexpr int NTILES = 1024;
+constexpr int NSCALES = 6;
+constexpr int TOTPIX = 87360;              // 65536+16384+4096+1024+256+64
+constexpr int EVAL_XYB_FLOATS = 3 * TOTPIX;  // positive-XYB pyramid of one evaluation
+constexpr int NSEG = 8;                    // <= 8 column segments (warps) per plane row
+constexpr int NSUMS = 6;                   // ssim d, d^4; edge artifact, artifact^4, detail_lost, detail_lost^4
+constexpr int PART_DOUBLES = NSCALES * 3 * NSEG * NSUMS;
+constexpr int MAX_ENTRIES = 256;           // sub_count * sub_size
+constexpr int BLACK = 256;                 // table slot of a transparent (rendered black) pixel
+constexpr int NES_COUNT = 56;
+
+__host__ __device__ __forceinline__ int scale_off(int s) {  // pixel offset of scale s inside a pyramid
+    // sum_{t<s} (256>>t)^2 = 65536 * (1 - 4^-s) * 4/3 : 0, 65536, 81920, 86016, 87040, 87296, 87360
+    return (262144 - (262144 >> (2 * s))) / 3;
+}
+
+// Per-image base tables for every palette entry (+ slot 256 = black), rebuilt whenever the palette changes.
+struct PalTables {
+    float lin[MAX_ENTRIES + 1][3];  // linear RGB of as_rgba(entry)
+    float xyb[MAX_ENTRIES + 1][3];  // positive XYB of the same
+    uchar4 rgb8[MAX_ENTRIES];       // SnesColor::as_rgba (lib.rs:662-669), u8-wrapping
+    float lab[MAX_ENTRIES][4];      // Lab<D65,f32> of rgb8 (perceptual mode)
+};
+
+// The one palette entry a candidate replaces.
+struct CandEntry {
+    float lin[3];
+    float xyb[3];
+    uchar4 rgb8;
+    float lab[3];
+    uint32_t pad[2];
+};
+
+// Device view of one OptimizedImage.
+struct ImgDev {
+    const uchar4 *rgba;       // original, row-major
+    uint8_t *tile_pal;        // 1024
+    uint8_t *palette;         // C*S*3, "5-bit" values
+    uint8_t *map;             // palette_map
+    const float *xyb_rm;      // source positive-XYB pyramid [scale][ch][y][x]
+    const float *xyb_cm;      // same, transposed [scale][ch][x][y]
+    float *mu1;               // blur(i1)       [scale][ch][y][x]
+    float *s11;               // blur(i1*i1)    [scale][ch][y][x]
+    PalTables *tables;
+    double *cur_err;          // error() of the current state
+    const float *lab;         // per-pixel Lab of the original (perceptual mode), [NPIX][4]
+};
+
+struct Best {
+    double err;
+    int32_t idx;
+    int32_t pad;
+};
+
+// ---- colour helpers -----------------------------------------------------------------------------
+__device__ __forceinline__ uchar4 snes_as_rgba(uint8_t r, uint8_t g, uint8_t b) {  // lib.rs:662-669
+    return make_uchar4((uint8_t)((uint8_t)(r * 8) + r / 4), (uint8_t)((uint8_t)(g * 8) + g / 4),
+                       (uint8_t)((uint8_t)(b * 8) + b / 4), 255);
+}
+
+// lib.rs:1080-1088 as an order-equivalent int32 key (= 512 * distance^2): the f64 expression is exact
+// for u8 operands and sqrt is monotone, so `<` and ties on the key are those of the reference.
+__device__ __forceinline__ int redmean_key(int r1, int g1, int b1, int r2, int g2, int b2) {
+    const int rs = r1 + r2, dr = r1 - r2, dg = g1 - g2, db = b1 - b2;
+    return (1024 + rs) * dr * dr + 2048 * dg * dg + (1534 - rs) * db * db;
+}
+
+// FreeBSD msun s_cbrtf.c (as ported by yuvxyb-math): bit-exact restatement, f64 Halley steps.
+__device__ __forceinline__ float msun_cbrtf(float x) {
+    const uint32_t B1 = 709958130u, B2 = 642849266u;
+    uint32_t bits = __float_as_uint(x);
+    uint32_t hx = bits & 0x7fffffffu;
+    const uint32_t sign = bits & 0x80000000u;
+    if (hx >= 0x7f800000u) return x + x;
+    if (hx < 0x00800000u) {
+        if (hx == 0) return x;
+        hx = __float_as_uint(x * 16777216.0f) & 0x7fffffffu;
+        hx = hx / 3 + B2;
+    } else {
+        hx = hx / 3 + B1;
+    }
+    double t = (double)__uint_as_float(sign | hx);
+    const double xd = (double)x;
+    double r = t * t * t;
+    t = t * (xd + xd + r) / (xd + r + r);
+    r = t * t * t;
+    t = t * (xd + xd + r) / (xd + r + r);
+    return (float)t;
+}
+
+// yuvxyb linear_rgb_to_xyb + ssimulacra2 make_positive_xyb
+__device__ __forceinline__ void lin_to_pxyb(float r, float g, float b, float &X, float &Y, float &B) {
+    const float kM02 = 0.078f, kM00 = 0.30f, kM01 = 1.0f - kM02 - kM00;
+    const float kM12 = 0.078f, kM10 = 0.23f, kM11 = 1.0f - kM12 - kM10;
+    const float kM20 = 0.24342269f, kM21 = 0.20476745f, kM22 = 1.0f - kM20 - kM21;
+    const float kB0 = 0.0037930734f;
+    const float kNegBias = -0.15595420f;
+    float m0 = __fmaf_rn(kM00, r, __fmaf_rn(kM01, g, __fmaf_rn(kM02, b, kB0)));
+    float m1 = __fmaf_rn(kM10, r, __fmaf_rn(kM11, g, __fmaf_rn(kM12, b, kB0)));
+    float m2 = __fmaf_rn(kM20, r, __fmaf_rn(kM21, g, __fmaf_rn(kM22, b, kB0)));
+    m0 = m0 < 0.0f ? 0.0f : m0;
+    m1 = m1 < 0.0f ? 0.0f : m1;
+    m2 = m2 < 0.0f ? 0.0f : m2;
+    m0 = msun_cbrtf(m0) + kNegBias;
+    m1 = msun_cbrtf(m1) + kNegBias;
+    m2 = msun_cbrtf(m2) + kNegBias;
+    const float x = 0.5f * (m0 - m1), y = 0.5f * (m0 + m1);
+    B = (m2 - y) + 0.55f;
+    X = __fmaf_rn(x, 14.0f, 0.42f);
+    Y = y + 0.01f;
+}
+
+}  // namespace snes

@@ -1,0 +1,1072 @@
+// libsnesgpu.so -- C ABI (include/snesgpu.h) over the sm_100a kernels.
+//
+// Host side only orchestrates: it owns device buffers, builds the small constant tables (sRGB
+// transfer LUTs, recursive-Gaussian taps, pooling weights, NES colours), launches kernels on one
+// stream and copies state in and out.  Every arithmetic step of the hot path runs on the GPU; there
+// is no CPU fallback -- without a usable sm_100 device every compute entry point returns SNES_E_CUDA.
+#include "../../include/snesgpu.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "dither.cuh"
+#include "kernels.cuh"
+#include "kmeans.cuh"
+#include "lab.cuh"
+
+using namespace snes;
+
+static_assert(sizeof(Best) == sizeof(snes_best), "snes_best layout");
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(SNES_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                 \
+    } while (0)
+#define RET(call)                 \
+    do {                          \
+        int r_ = (call);          \
+        if (r_ != SNES_OK) return r_; \
+    } while (0)
+
+extern "C" const char *snes_last_error(void) { return g_err.c_str(); }
+extern "C" int snes_version(void) { return 1; }
+
+// ------------------------------------------------------------------------------------------------
+// context / image
+// ------------------------------------------------------------------------------------------------
+struct snes_ctx {
+    int device = 0;
+    cudaStream_t own = nullptr, stream = nullptr;
+    int64_t launches = 0;
+    int chunk = 16;  // evaluations whose intermediates are live at once (sized to stay L2-resident)
+
+    // per-chunk scratch
+    size_t chunk_cap = 0;
+    float *xyb_rm = nullptr, *xyb_cm = nullptr, *hbuf = nullptr;
+    uint8_t *maps = nullptr;
+    // per-batch scratch
+    size_t eval_cap = 0;
+    double *partials = nullptr, *scores = nullptr;
+    CandEntry *cents = nullptr;
+    uint8_t *cand = nullptr;
+    size_t img_cap = 0;
+    ImgDev *d_imgs = nullptr;
+    KmScratch *d_km = nullptr;
+    Best *best = nullptr;
+    double *self_scores = nullptr;
+    std::vector<snes_image *> cached;
+
+    float4 *labtab = nullptr;  // BGR555 -> Lab<D65,f32>
+};
+
+struct snes_image {
+    snes_ctx *ctx = nullptr;
+    snes_config cfg{};
+    ImgDev dev{};
+    KmScratch km{};
+    void *slab = nullptr, *km_slab = nullptr;
+    std::vector<uint8_t> alpha;  // host copy of the alpha channel (as_json)
+};
+
+static int set_device(snes_ctx *ctx) {
+    CK(cudaSetDevice(ctx->device));
+    return SNES_OK;
+}
+
+template <typename T>
+static int dev_alloc(T **p, size_t n) {
+    CK(cudaMalloc((void **)p, n * sizeof(T)));
+    return SNES_OK;
+}
+
+static float srgb_eotf_yuvxyb(float x) {  // yuvxyb transfer: sRGB -> linear
+    const float alpha = 1.0550107f, beta = 0.0030412825f;
+    x = x > 0.0f ? x : 0.0f;
+    if (x < 12.92f * beta) return x / 12.92f;
+    return powf((x + (alpha - 1.0f)) / alpha, 2.4f);
+}
+
+static void inv3x3(double m[9]) {
+    const double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+    const double A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
+    const double inv = 1.0 / (a * A + b * B + c * C);
+    m[0] = A * inv;
+    m[1] = -(b * i - c * h) * inv;
+    m[2] = (b * f - c * e) * inv;
+    m[3] = B * inv;
+    m[4] = (a * i - c * g) * inv;
+    m[5] = -(a * f - c * d) * inv;
+    m[6] = C * inv;
+    m[7] = -(a * h - b * g) * inv;
+    m[8] = (a * e - b * d) * inv;
+}
+
+// libjxl CreateRecursiveGaussian(sigma = 1.5): Charalampidis 2016, three second-order sections.
+static void gaussian_taps(float n2[3], float d1[3]) {
+    const double sigma = 1.5, pi = 3.141592653589793238;
+    const double radius = std::round(3.2795 * sigma + 0.2546);
+    const double w = pi / (2.0 * radius);
+    const double omega[3] = {w, 3.0 * w, 5.0 * w};
+    const double p1 = 1.0 / std::tan(0.5 * omega[0]), p3 = -1.0 / std::tan(0.5 * omega[1]), p5 = 1.0 / std::tan(0.5 * omega[2]);
+    const double r1 = p1 * p1 / std::sin(omega[0]), r3 = -p3 * p3 / std::sin(omega[1]), r5 = p5 * p5 / std::sin(omega[2]);
+    double rho[3];
+    for (int i = 0; i < 3; i++) rho[i] = std::exp(-0.5 * sigma * sigma * omega[i] * omega[i]) * (1.0 / radius);
+    const double D13 = p1 * r3 - r1 * p3, D35 = p3 * r5 - r3 * p5, D51 = p5 * r1 - r5 * p1;
+    const double rd13 = 1.0 / D13, z15 = D35 * rd13, z35 = D51 * rd13;
+    double A[9] = {p1, p3, p5, r1, r3, r5, z15, z35, 1.0};
+    inv3x3(A);
+    const double gamma[3] = {1.0, radius * radius - sigma * sigma, z15 * rho[0] + z35 * rho[1] + rho[2]};
+    for (int i = 0; i < 3; i++) {
+        const double beta = A[3 * i] * gamma[0] + A[3 * i + 1] * gamma[1] + A[3 * i + 2] * gamma[2];
+        n2[i] = (float)(-beta * std::cos(omega[i] * (radius + 1.0)));
+        d1[i] = (float)(-2.0 * std::cos(omega[i]));
+    }
+}
+
+static const double kWeights[108] = {
+    0.0, 0.0007376606707406586, 0.0, 0.0, 0.0007793481682867309, 0.0, 0.0, 0.0004371155730107379, 0.0,
+    1.1041726426657346, 0.00066284834129271, 0.00015231632783718752, 0.0, 0.0016406437456599754, 0.0,
+    1.8422455520539298, 11.441172603757666, 0.0, 0.0007989109436015163, 0.000176816438078653, 0.0,
+    1.8787594979546387, 10.94906990605142, 0.0, 0.0007289346991508072, 0.9677937080626833, 0.0,
+    0.00014003424285435884, 0.9981766977854967, 0.00031949755934435053, 0.0004550992113792063, 0.0, 0.0,
+    0.0013648766163243398, 0.0, 0.0, 0.0, 0.0, 0.0, 7.466890328078848, 0.0, 17.445833984131262,
+    0.0006235601634041466, 0.0, 0.0, 6.683678146179332, 0.00037724407979611296, 1.027889937768264,
+    225.20515300849274, 0.0, 0.0, 19.213238186143016, 0.0011401524586618361, 0.001237755635509985,
+    176.39317598450694, 0.0, 0.0, 24.43300999870476, 0.28520802612117757, 0.0004485436923833408, 0.0, 0.0, 0.0,
+    34.77906344483772, 44.835625328877896, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0008680556573291698, 0.0, 0.0, 0.0,
+    0.0, 0.0, 0.0005313191874358747, 0.0, 0.00016533814161379112, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0004179171803251336,
+    0.0017290828234722833, 0.0, 0.0020827005846636437, 0.0, 0.0, 8.826982764996862, 23.19243343998926, 0.0,
+    95.1080498811086, 0.9863978034400682, 0.9834382792465353, 0.0012286405048278493, 171.2667255897307,
+    0.9807858872435379, 0.0, 0.0, 0.0, 0.0005130064588990679, 0.0, 0.00010854057858411537};
+
+static const uint8_t kNes[NES_COUNT][3] = {  // lib.rs:687-742
+    {13, 13, 13}, {0, 2, 16},   {3, 0, 17},   {7, 0, 15},   {10, 0, 10},  {11, 0, 3},   {9, 2, 0},    {7, 3, 0},
+    {4, 6, 0},    {0, 7, 0},    {0, 8, 0},    {0, 7, 4},    {0, 5, 10},   {0, 0, 0},    {23, 23, 23}, {3, 10, 24},
+    {9, 6, 28},   {14, 4, 26},  {18, 3, 21},  {19, 5, 11},  {19, 6, 0},   {15, 9, 0},   {11, 12, 0},  {4, 14, 0},
+    {0, 15, 0},   {0, 14, 8},   {0, 13, 17},  {0, 0, 0},    {31, 31, 31}, {13, 20, 31}, {17, 19, 31}, {22, 16, 31},
+    {27, 14, 31}, {28, 14, 23}, {28, 17, 13}, {26, 19, 5},  {22, 21, 1},  {15, 24, 2},  {10, 25, 8},  {8, 25, 16},
+    {8, 24, 24},  {9, 9, 9},    {31, 31, 31}, {25, 29, 31}, {27, 27, 31}, {29, 27, 31}, {31, 26, 31}, {31, 26, 30},
+    {31, 27, 25}, {31, 28, 22}, {30, 30, 21}, {27, 31, 21}, {25, 31, 23}, {24, 31, 26}, {24, 30, 30}, {23, 24, 23}};
+
+static constexpr int kBlurHSmem0 = 4 * 3 * 32 * 33 * (int)sizeof(float);
+static constexpr int kBlurHSmem1 = 4 * 2 * 32 * 33 * (int)sizeof(float);
+
+extern "C" int snes_ctx_create(int device, snes_ctx **out) {
+    if (!out) return fail(SNES_E_INVALID, "snes_ctx_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(SNES_E_CUDA, "snes_ctx_create: no such CUDA device");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(SNES_E_CUDA, std::string("snes_ctx_create: libsnesgpu is built for sm_100a only; device is ") + prop.name);
+    snes_ctx *ctx = new snes_ctx();
+    ctx->device = device;
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&ctx->own, cudaStreamNonBlocking));
+    ctx->stream = ctx->own;
+    if (const char *c = getenv("SNESGPU_CHUNK")) {
+        const int v = atoi(c);
+        if (v > 0) ctx->chunk = v;
+    }
+
+    float lut[256], lut2[256], n2[3], d1[3];
+    for (int v = 0; v < 256; v++) {
+        lut[v] = srgb_eotf_yuvxyb((float)v / 255.0f);
+        const float c = (float)v / 255.0f;  // palette: Srgb<u8>::into_format, Srgb::into_linear
+        lut2[v] = c <= 0.04045f ? c / 12.92f : powf((c + 0.055f) / 1.055f, 2.4f);
+    }
+    gaussian_taps(n2, d1);
+    uint8_t nes4[NES_COUNT][4];
+    for (int i = 0; i < NES_COUNT; i++) {
+        nes4[i][0] = kNes[i][0];
+        nes4[i][1] = kNes[i][1];
+        nes4[i][2] = kNes[i][2];
+        nes4[i][3] = 0;
+    }
+    CK(cudaMemcpyToSymbol(c_lin_lut, lut, sizeof(lut)));
+    CK(cudaMemcpyToSymbol(c_srgb_lin_lut, lut2, sizeof(lut2)));
+    CK(cudaMemcpyToSymbol(c_n2, n2, sizeof(n2)));
+    CK(cudaMemcpyToSymbol(c_d1, d1, sizeof(d1)));
+    CK(cudaMemcpyToSymbol(c_weight, kWeights, sizeof(kWeights)));
+    CK(cudaMemcpyToSymbol(c_nes, nes4, sizeof(nes4)));
+    CK(cudaFuncSetAttribute(k_blur_h<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlurHSmem0));
+    CK(cudaFuncSetAttribute(k_blur_h<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlurHSmem1));
+
+    RET(dev_alloc(&ctx->labtab, 32768));
+    k_build_lab_table<<<128, 256, 0, ctx->stream>>>(ctx->labtab);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    *out = ctx;
+    return SNES_OK;
+}
+
+static void free_scratch(snes_ctx *ctx) {
+    cudaFree(ctx->xyb_rm);
+    cudaFree(ctx->xyb_cm);
+    cudaFree(ctx->hbuf);
+    cudaFree(ctx->maps);
+    cudaFree(ctx->partials);
+    cudaFree(ctx->scores);
+    cudaFree(ctx->cents);
+    cudaFree(ctx->cand);
+    cudaFree(ctx->d_imgs);
+    cudaFree(ctx->d_km);
+    cudaFree(ctx->best);
+    cudaFree(ctx->self_scores);
+}
+
+extern "C" void snes_ctx_destroy(snes_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_scratch(ctx);
+    cudaFree(ctx->labtab);
+    cudaStreamDestroy(ctx->own);
+    delete ctx;
+}
+
+extern "C" int64_t snes_ctx_kernel_launches(const snes_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int snes_ctx_set_stream(snes_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return fail(SNES_E_INVALID, "ctx is NULL");
+    RET(set_device(ctx));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own;
+    return SNES_OK;
+}
+
+extern "C" int snes_ctx_synchronize(snes_ctx *ctx) {
+    if (!ctx) return fail(SNES_E_INVALID, "ctx is NULL");
+    RET(set_device(ctx));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SNES_OK;
+}
+
+extern "C" int snes_ctx_set_chunk(snes_ctx *ctx, int evaluations) {
+    if (!ctx || evaluations < 1) return fail(SNES_E_INVALID, "snes_ctx_set_chunk: bad argument");
+    ctx->chunk = evaluations;
+    return SNES_OK;
+}
+
+// ---- scratch management ------------------------------------------------------------------------
+static int ensure_chunk(snes_ctx *ctx, size_t n) {
+    if (n <= ctx->chunk_cap) return SNES_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->xyb_rm);
+    cudaFree(ctx->xyb_cm);
+    cudaFree(ctx->hbuf);
+    cudaFree(ctx->maps);
+    ctx->xyb_rm = ctx->xyb_cm = ctx->hbuf = nullptr;
+    ctx->maps = nullptr;
+    ctx->chunk_cap = 0;
+    RET(dev_alloc(&ctx->xyb_rm, n * EVAL_XYB_FLOATS));
+    RET(dev_alloc(&ctx->xyb_cm, n * EVAL_XYB_FLOATS));
+    RET(dev_alloc(&ctx->hbuf, n * EVAL_XYB_FLOATS * 3));
+    RET(dev_alloc(&ctx->maps, n * NPIX));
+    ctx->chunk_cap = n;
+    return SNES_OK;
+}
+
+static int ensure_evals(snes_ctx *ctx, size_t n) {
+    if (n <= ctx->eval_cap) return SNES_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->partials);
+    cudaFree(ctx->scores);
+    cudaFree(ctx->cents);
+    cudaFree(ctx->cand);
+    ctx->partials = ctx->scores = nullptr;
+    ctx->cents = nullptr;
+    ctx->cand = nullptr;
+    ctx->eval_cap = 0;
+    RET(dev_alloc(&ctx->partials, n * PART_DOUBLES));
+    RET(dev_alloc(&ctx->scores, n));
+    RET(dev_alloc(&ctx->cents, n));
+    RET(dev_alloc(&ctx->cand, n * 3));
+    ctx->eval_cap = n;
+    return SNES_OK;
+}
+
+static int ensure_imgs(snes_ctx *ctx, size_t n) {
+    if (n <= ctx->img_cap) return SNES_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_imgs);
+    cudaFree(ctx->d_km);
+    cudaFree(ctx->best);
+    cudaFree(ctx->self_scores);
+    ctx->d_imgs = nullptr;
+    ctx->d_km = nullptr;
+    ctx->best = nullptr;
+    ctx->self_scores = nullptr;
+    ctx->img_cap = 0;
+    ctx->cached.clear();
+    RET(dev_alloc(&ctx->d_imgs, n));
+    RET(dev_alloc(&ctx->d_km, n));
+    RET(dev_alloc(&ctx->best, n));
+    RET(dev_alloc(&ctx->self_scores, n));
+    ctx->img_cap = n;
+    return SNES_OK;
+}
+
+// Validate a batch (same context, same config) and make ctx->d_imgs describe it.
+static int bind_images(snes_ctx *ctx, snes_image *const *images, int nimg) {
+    if (!ctx || !images || nimg < 1) return fail(SNES_E_INVALID, "batch: no images");
+    for (int j = 0; j < nimg; j++) {
+        if (!images[j] || images[j]->ctx != ctx) return fail(SNES_E_INVALID, "batch: image belongs to another context");
+        if (memcmp(&images[j]->cfg, &images[0]->cfg, sizeof(snes_config)) != 0)
+            return fail(SNES_E_INVALID, "batch: all images of a batch must share one config");
+    }
+    RET(set_device(ctx));
+    RET(ensure_imgs(ctx, (size_t)nimg));
+    if ((int)ctx->cached.size() == nimg && memcmp(ctx->cached.data(), images, sizeof(snes_image *) * nimg) == 0) return SNES_OK;
+    std::vector<ImgDev> h(nimg);
+    for (int j = 0; j < nimg; j++) h[j] = images[j]->dev;
+    CK(cudaMemcpyAsync(ctx->d_imgs, h.data(), sizeof(ImgDev) * nimg, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->cached.assign(images, images + nimg);
+    return SNES_OK;
+}
+
+#define LAUNCHED(ctx)               \
+    do {                            \
+        (ctx)->launches++;          \
+        CK(cudaGetLastError());     \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// the evaluation pipeline
+// ------------------------------------------------------------------------------------------------
+struct EvalPlan {
+    int nimg = 0;
+    int ncand = 1;                    // evaluations per image
+    int ovr = -1;                     // palette slot replaced by the candidate colour, -1: none
+    const uint8_t *d_cand = nullptr;  // [nimg*ncand][3] device, required when ovr >= 0
+    bool self = false;                // operate on the images' own palette_map instead of scratch maps
+    bool do_assign = false;           // optimize()
+    bool do_score = false;            // error()
+    uint8_t *d_maps_out = nullptr;    // optional [E][NPIX] device: keep every palette_map
+    double *d_scores = nullptr;       // [E] device output of do_score
+};
+
+// Requires bind_images() first.
+static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
+    const int E = pl.nimg * pl.ncand, S = cfg.subpalette_size, CS = cfg.subpalette_count * cfg.subpalette_size;
+    cudaStream_t st = ctx->stream;
+    RET(ensure_evals(ctx, (size_t)E));
+    const int chunk = E < ctx->chunk ? E : ctx->chunk;
+    if (pl.do_score || (pl.do_assign && !pl.self && !pl.d_maps_out)) RET(ensure_chunk(ctx, (size_t)chunk));
+    const float4 *labtab = cfg.perceptual_palettes ? ctx->labtab : nullptr;
+
+    k_tables<<<pl.nimg + (pl.ovr >= 0 ? (E + 255) / 256 : 0), 256, 0, st>>>(ctx->d_imgs, pl.nimg, CS, pl.d_cand,
+                                                                          pl.ovr >= 0 ? E : 0, ctx->cents, labtab);
+    LAUNCHED(ctx);
+
+    for (int e0 = 0; e0 < E; e0 += chunk) {
+        const int ec = E - e0 < chunk ? E - e0 : chunk;
+        uint8_t *maps = pl.d_maps_out ? pl.d_maps_out + (size_t)e0 * NPIX : ctx->maps;
+        if (pl.do_assign) {
+            if (cfg.dither) {
+                if (cfg.perceptual_palettes)
+                    k_assign_dither<true><<<ec, 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self);
+                else
+                    k_assign_dither<false><<<ec, 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self);
+            } else if (cfg.perceptual_palettes) {
+                k_assign_lab<<<dim3(64, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self);
+            } else {
+                k_assign_rgb<<<dim3(64, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self);
+            }
+            LAUNCHED(ctx);
+        }
+        if (!pl.do_score) continue;
+        k_pyramid<false><<<dim3(16, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self,
+                                                       ctx->xyb_rm, ctx->xyb_cm);
+        LAUNCHED(ctx);
+        for (int s = 0; s < NSCALES; s++) {
+            const int d = W >> s, lines = ec * 3 * d;
+            k_blur_h<0><<<(lines + 127) / 128, 128, kBlurHSmem0, st>>>(s, lines, ctx->d_imgs, pl.ncand, e0, ctx->xyb_cm, ctx->hbuf);
+            LAUNCHED(ctx);
+            k_blur_v<0><<<(lines + 127) / 128, 128, 0, st>>>(s, lines, ctx->d_imgs, pl.ncand, e0, ctx->xyb_rm, ctx->hbuf,
+                                                           ctx->partials);
+            LAUNCHED(ctx);
+        }
+    }
+    if (pl.do_score) {
+        k_pool<<<(E + 127) / 128, 128, 0, st>>>(ctx->partials, E, pl.d_scores);
+        LAUNCHED(ctx);
+    }
+    return SNES_OK;
+}
+
+// optimize() of every image in the batch (lib.rs:425-501)
+static int batch_optimize(snes_ctx *ctx, snes_image *const *images, int nimg) {
+    RET(bind_images(ctx, images, nimg));
+    EvalPlan pl;
+    pl.nimg = nimg;
+    pl.self = true;
+    pl.do_assign = true;
+    return run_plan(ctx, images[0]->cfg, pl);
+}
+
+// error() of every image in the batch (lib.rs:503-548) -> cur_err of each image (and ctx->self_scores)
+static int batch_error(snes_ctx *ctx, snes_image *const *images, int nimg) {
+    RET(bind_images(ctx, images, nimg));
+    EvalPlan pl;
+    pl.nimg = nimg;
+    pl.self = true;
+    pl.do_score = true;
+    pl.d_scores = ctx->self_scores;
+    RET(run_plan(ctx, images[0]->cfg, pl));
+    k_store_cur_err<<<(nimg + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_imgs, nimg, ctx->self_scores);
+    LAUNCHED(ctx);
+    return SNES_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// OptimizedImage
+// ------------------------------------------------------------------------------------------------
+static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+extern "C" int snes_image_new(snes_ctx *ctx, const uint8_t *rgba, int width, int height, const snes_config *cfg, snes_image **out) {
+    if (!ctx || !rgba || !cfg || !out) return fail(SNES_E_INVALID, "snes_image_new: NULL argument");
+    *out = nullptr;
+    // lib.rs:838-840 lets any image with one side of 256 through, after which its fixed 32x32 tile
+    // table (lib.rs:58, 565) is wrong; only 256x256 is accepted here.
+    if (width != SNES_WIDTH || height != SNES_HEIGHT) return fail(SNES_E_INVALID, "Image must be 256x256");
+    const int C = cfg->subpalette_count, S = cfg->subpalette_size;
+    if (C < 1 || S < 1 || C > 255 || S > 255 || C * S > MAX_ENTRIES)
+        return fail(SNES_E_INVALID, "snes_image_new: need 1 <= subpalette_count*subpalette_size <= 256");
+    RET(set_device(ctx));
+    snes_image *im = new snes_image();
+    im->ctx = ctx;
+    im->cfg = *cfg;
+    im->cfg.dither = cfg->dither ? 1 : 0;
+    im->cfg.perceptual_palettes = cfg->perceptual_palettes ? 1 : 0;
+    im->cfg.nes = cfg->nes ? 1 : 0;
+    im->cfg.reserved = 0;
+    im->alpha.resize(NPIX);
+    for (int i = 0; i < NPIX; i++) im->alpha[i] = rgba[4 * i + 3];
+
+    const size_t plane = align_up(sizeof(float) * EVAL_XYB_FLOATS);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        const size_t o = off;
+        off += align_up(bytes);
+        return o;
+    };
+    const size_t o_rgba = take(NPIX * 4), o_tp = take(NTILES), o_pal = take(MAX_ENTRIES * 3), o_map = take(NPIX);
+    const size_t o_rm = take(plane), o_cm = take(plane), o_mu = take(plane), o_s11 = take(plane);
+    const size_t o_tab = take(sizeof(PalTables)), o_err = take(sizeof(double));
+    const size_t o_lab = take(im->cfg.perceptual_palettes ? sizeof(float4) * NPIX : 0);
+    cudaError_t e = cudaMalloc(&im->slab, off);
+    if (e != cudaSuccess) {
+        delete im;
+        return fail(SNES_E_NOMEM, std::string("snes_image_new: cudaMalloc: ") + cudaGetErrorString(e));
+    }
+    char *b = (char *)im->slab;
+    im->dev.rgba = (const uchar4 *)(b + o_rgba);
+    im->dev.tile_pal = (uint8_t *)(b + o_tp);
+    im->dev.palette = (uint8_t *)(b + o_pal);
+    im->dev.map = (uint8_t *)(b + o_map);
+    im->dev.xyb_rm = (const float *)(b + o_rm);
+    im->dev.xyb_cm = (const float *)(b + o_cm);
+    im->dev.mu1 = (float *)(b + o_mu);
+    im->dev.s11 = (float *)(b + o_s11);
+    im->dev.tables = (PalTables *)(b + o_tab);
+    im->dev.cur_err = (double *)(b + o_err);
+    im->dev.lab = im->cfg.perceptual_palettes ? (const float *)(b + o_lab) : nullptr;
+
+    cudaStream_t st = ctx->stream;
+    int rc = SNES_OK;
+    auto body = [&]() -> int {
+        CK(cudaMemsetAsync(im->slab, 0, o_rm, st));  // tile_palettes, palette (Palette::new: all black), palette_map = 0
+        CK(cudaMemsetAsync(b + o_tab, 0, sizeof(PalTables), st));
+        CK(cudaMemsetAsync(b + o_err, 0, sizeof(double), st));
+        CK(cudaMemcpyAsync(b + o_rgba, rgba, NPIX * 4, cudaMemcpyHostToDevice, st));
+        if (im->cfg.perceptual_palettes) {
+            k_image_lab<<<256, 256, 0, st>>>(im->dev.rgba, (float4 *)(b + o_lab));
+            LAUNCHED(ctx);
+        }
+        // source side of SSIMULACRA2, once per image: XYB pyramid, mu1 = blur(i1), s11 = blur(i1*i1)
+        snes_image *one[1] = {im};
+        RET(bind_images(ctx, one, 1));
+        RET(ensure_chunk(ctx, 1));
+        k_pyramid<true><<<dim3(16, 1), 256, 0, st>>>(ctx->d_imgs, nullptr, 1, 0, 0, 0, -1, nullptr, 0, nullptr, nullptr);
+        LAUNCHED(ctx);
+        for (int s = 0; s < NSCALES; s++) {
+            const int d = W >> s, lines = 3 * d;
+            k_blur_h<1><<<(lines + 127) / 128, 128, kBlurHSmem1, st>>>(s, lines, ctx->d_imgs, 1, 0, nullptr, ctx->hbuf);
+            LAUNCHED(ctx);
+            k_blur_v<1><<<(lines + 127) / 128, 128, 0, st>>>(s, lines, ctx->d_imgs, 1, 0, nullptr, ctx->hbuf, nullptr);
+            LAUNCHED(ctx);
+        }
+        CK(cudaStreamSynchronize(st));
+        return SNES_OK;
+    };
+    rc = body();
+    if (rc != SNES_OK) {
+        ctx->cached.clear();
+        cudaFree(im->slab);
+        delete im;
+        return rc;
+    }
+    *out = im;
+    return SNES_OK;
+}
+
+extern "C" void snes_image_free(snes_image *im) {
+    if (!im) return;
+    snes_ctx *ctx = im->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->cached.clear();
+    cudaFree(im->slab);
+    cudaFree(im->km_slab);
+    delete im;
+}
+
+static int ensure_km(snes_image *im) {
+    if (im->km_slab) return SNES_OK;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        const size_t o = off;
+        off += align_up(bytes);
+        return o;
+    };
+    const size_t o_pts = take(sizeof(float) * 3 * NPIX), o_asg = take(sizeof(int) * NPIX), o_off = take(sizeof(int) * 260);
+    const size_t o_means = take(sizeof(double) * 3 * NTILES), o_tm = take(sizeof(int) * NTILES), o_n = take(sizeof(int));
+    const size_t o_cent = take(sizeof(double) * 3 * KM_MAXK), o_st = take(sizeof(int) * 2 * 256);
+    CK(cudaMalloc(&im->km_slab, off));
+    char *b = (char *)im->km_slab;
+    im->km.pts = (float *)(b + o_pts);
+    im->km.assign = (int *)(b + o_asg);
+    im->km.sub_off = (int *)(b + o_off);
+    im->km.means = (double *)(b + o_means);
+    im->km.tile_map = (int *)(b + o_tm);
+    im->km.nmeans = (int *)(b + o_n);
+    im->km.centres = (double *)(b + o_cent);
+    im->km.status = (int *)(b + o_st);
+    return SNES_OK;
+}
+
+static int bind_km(snes_ctx *ctx, snes_image *const *images, int nimg) {
+    std::vector<KmScratch> h(nimg);
+    for (int j = 0; j < nimg; j++) {
+        RET(ensure_km(images[j]));
+        h[j] = images[j]->km;
+    }
+    CK(cudaMemcpyAsync(ctx->d_km, h.data(), sizeof(KmScratch) * nimg, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SNES_OK;
+}
+
+// recalculate_palette(p) for every subpalette of every image (lib.rs:330-405); first < 0 status wins.
+static int batch_recalc(snes_ctx *ctx, snes_image *const *images, int nimg, int only_sub0) {
+    const snes_config cfg = images[0]->cfg;
+    const int C = only_sub0 ? 1 : cfg.subpalette_count, S = cfg.subpalette_size;
+    cudaStream_t st = ctx->stream;
+    k_gather_points<<<nimg, 1024, 0, st>>>(ctx->d_imgs, ctx->d_km, cfg.subpalette_count, cfg.perceptual_palettes);
+    LAUNCHED(ctx);
+    for (int j = 0; j < nimg; j++) CK(cudaMemsetAsync(images[j]->km.status, 0xff, sizeof(int) * 2 * 256, st));
+    // grid is (image, subpalette) with C as the stride; with only_sub0 the grid covers subpalette 0 only
+    k_kmeans<false><<<nimg * C, 1024, 0, st>>>(ctx->d_imgs, ctx->d_km, C, S);
+    LAUNCHED(ctx);
+    k_centres_to_palette<<<nimg, 256, 0, st>>>(ctx->d_imgs, ctx->d_km, C, S, cfg.perceptual_palettes, cfg.nes, ctx->labtab, 0);
+    LAUNCHED(ctx);
+    std::vector<int> status(C);
+    for (int j = 0; j < nimg; j++) {
+        CK(cudaMemcpyAsync(status.data(), images[j]->km.status, sizeof(int) * C, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int p = 0; p < C; p++)
+            if (status[p] != 0) return fail(SNES_E_KMEANS, "cogset Kmeans::new: assertion failed: 2 <= k && k < data.len()");
+    }
+    return SNES_OK;
+}
+
+extern "C" int snes_batch_recalculate_palettes(snes_ctx *ctx, snes_image *const *images, int nimg) {
+    RET(bind_images(ctx, images, nimg));
+    RET(bind_km(ctx, images, nimg));
+    RET(batch_recalc(ctx, images, nimg, 0));
+    RET(batch_optimize(ctx, images, nimg));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SNES_OK;
+}
+
+extern "C" int snes_batch_initialize_tiles(snes_ctx *ctx, snes_image *const *images, int nimg) {
+    RET(bind_images(ctx, images, nimg));
+    RET(bind_km(ctx, images, nimg));
+    const snes_config cfg = images[0]->cfg;
+    cudaStream_t st = ctx->stream;
+    if (cfg.subpalette_count == 1) {  // lib.rs:80-84
+        RET(batch_recalc(ctx, images, nimg, 1));
+    } else {
+        k_tile_means<<<nimg, 1024, 0, st>>>(ctx->d_imgs, ctx->d_km, cfg.perceptual_palettes);
+        LAUNCHED(ctx);
+        for (int j = 0; j < nimg; j++) CK(cudaMemsetAsync(images[j]->km.status, 0xff, sizeof(int) * 2 * 256, st));
+        k_kmeans<true><<<nimg, 1024, 0, st>>>(ctx->d_imgs, ctx->d_km, cfg.subpalette_count, cfg.subpalette_count);
+        LAUNCHED(ctx);
+        k_centres_to_palette<<<nimg, 256, 0, st>>>(ctx->d_imgs, ctx->d_km, cfg.subpalette_count, cfg.subpalette_size,
+                                                  cfg.perceptual_palettes, cfg.nes, ctx->labtab, 1);
+        LAUNCHED(ctx);
+        for (int j = 0; j < nimg; j++) {
+            int status = -1;
+            CK(cudaMemcpyAsync(&status, images[j]->km.status, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (status != 0) return fail(SNES_E_KMEANS, "cogset Kmeans::new: assertion failed: 2 <= k && k < data.len()");
+        }
+    }
+    RET(batch_optimize(ctx, images, nimg));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SNES_OK;
+}
+
+extern "C" int snes_image_initialize_tiles(snes_image *im) {
+    if (!im) return fail(SNES_E_INVALID, "image is NULL");
+    snes_image *one[1] = {im};
+    return snes_batch_initialize_tiles(im->ctx, one, 1);
+}
+
+extern "C" int snes_image_recalculate_palettes(snes_image *im) {
+    if (!im) return fail(SNES_E_INVALID, "image is NULL");
+    snes_image *one[1] = {im};
+    return snes_batch_recalculate_palettes(im->ctx, one, 1);
+}
+
+extern "C" int snes_batch_optimize(snes_ctx *ctx, snes_image *const *images, int nimg) {
+    RET(batch_optimize(ctx, images, nimg));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SNES_OK;
+}
+
+extern "C" int snes_image_optimize(snes_image *im) {
+    if (!im) return fail(SNES_E_INVALID, "image is NULL");
+    snes_image *one[1] = {im};
+    return snes_batch_optimize(im->ctx, one, 1);
+}
+
+extern "C" int snes_batch_error(snes_ctx *ctx, snes_image *const *images, int nimg, double *errors) {
+    RET(batch_error(ctx, images, nimg));
+    if (errors) CK(cudaMemcpyAsync(errors, ctx->self_scores, sizeof(double) * nimg, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SNES_OK;
+}
+
+extern "C" int snes_batch_error_dev(snes_ctx *ctx, snes_image *const *images, int nimg, double *d_errors) {
+    RET(batch_error(ctx, images, nimg));
+    if (d_errors) CK(cudaMemcpyAsync(d_errors, ctx->self_scores, sizeof(double) * nimg, cudaMemcpyDeviceToDevice, ctx->stream));
+    return SNES_OK;
+}
+
+extern "C" int snes_image_error(snes_image *im, double *err) {
+    if (!im || !err) return fail(SNES_E_INVALID, "snes_image_error: NULL argument");
+    snes_image *one[1] = {im};
+    return snes_batch_error(im->ctx, one, 1, err);
+}
+
+extern "C" int snes_image_as_rgba(snes_image *im, uint8_t *out_rgba) {
+    if (!im || !out_rgba) return fail(SNES_E_INVALID, "snes_image_as_rgba: NULL argument");
+    snes_ctx *ctx = im->ctx;
+    RET(set_device(ctx));
+    RET(ensure_chunk(ctx, 1));
+    uchar4 *tmp = reinterpret_cast<uchar4 *>(ctx->hbuf);
+    k_as_rgba<<<256, 256, 0, ctx->stream>>>(im->dev, im->cfg.subpalette_size, tmp);
+    LAUNCHED(ctx);
+    CK(cudaMemcpyAsync(out_rgba, tmp, NPIX * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SNES_OK;
+}
+
+// ---- state accessors ---------------------------------------------------------------------------
+static int d2h(snes_image *im, void *dst, const void *src, size_t n) {
+    if (!im || !dst) return fail(SNES_E_INVALID, "accessor: NULL argument");
+    RET(set_device(im->ctx));
+    CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, im->ctx->stream));
+    CK(cudaStreamSynchronize(im->ctx->stream));
+    return SNES_OK;
+}
+static int h2d(snes_image *im, void *dst, const void *src, size_t n) {
+    if (!im || !src) return fail(SNES_E_INVALID, "accessor: NULL argument");
+    RET(set_device(im->ctx));
+    CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, im->ctx->stream));
+    CK(cudaStreamSynchronize(im->ctx->stream));
+    return SNES_OK;
+}
+
+extern "C" int snes_image_get_palette(snes_image *im, uint8_t *out) {
+    return d2h(im, out, im ? im->dev.palette : nullptr, im ? (size_t)im->cfg.subpalette_count * im->cfg.subpalette_size * 3 : 0);
+}
+extern "C" int snes_image_set_palette(snes_image *im, const uint8_t *in) {
+    if (!im || !in) return fail(SNES_E_INVALID, "accessor: NULL argument");
+    const size_t n = (size_t)im->cfg.subpalette_count * im->cfg.subpalette_size * 3;
+    // SnesColor values are 5-bit; 32 can arise from round(v/8) (lib.rs:396-400) and is kept
+    for (size_t i = 0; i < n; i++)
+        if (in[i] > 32) return fail(SNES_E_INVALID, "snes_image_set_palette: colour component > 32");
+    return h2d(im, im->dev.palette, in, n);
+}
+extern "C" int snes_image_get_tile_palettes(snes_image *im, uint8_t *out) { return d2h(im, out, im ? im->dev.tile_pal : nullptr, NTILES); }
+extern "C" int snes_image_set_tile_palettes(snes_image *im, const uint8_t *in) {
+    if (!im || !in) return fail(SNES_E_INVALID, "accessor: NULL argument");
+    for (int i = 0; i < NTILES; i++)
+        if (in[i] >= im->cfg.subpalette_count) return fail(SNES_E_INVALID, "snes_image_set_tile_palettes: index >= subpalette_count");
+    return h2d(im, im->dev.tile_pal, in, NTILES);
+}
+extern "C" int snes_image_get_palette_map(snes_image *im, uint8_t *out) { return d2h(im, out, im ? im->dev.map : nullptr, NPIX); }
+extern "C" int snes_image_set_palette_map(snes_image *im, const uint8_t *in) {
+    if (!im || !in) return fail(SNES_E_INVALID, "accessor: NULL argument");
+    for (int i = 0; i < NPIX; i++)
+        if (in[i] >= im->cfg.subpalette_size) return fail(SNES_E_INVALID, "snes_image_set_palette_map: index >= subpalette_size");
+    return h2d(im, im->dev.map, in, NPIX);
+}
+
+// lib.rs:579-625 + serde_json Value::to_string(): compact, object keys in BTreeMap (sorted) order.
+extern "C" int snes_image_as_json(snes_image *im, char *buf, size_t cap, size_t *len) {
+    if (!im || !len) return fail(SNES_E_INVALID, "snes_image_as_json: NULL argument");
+    const int C = im->cfg.subpalette_count, S = im->cfg.subpalette_size;
+    std::vector<uint8_t> pal((size_t)C * S * 3), tp(NTILES), map(NPIX);
+    RET(snes_image_get_palette(im, pal.data()));
+    RET(snes_image_get_tile_palettes(im, tp.data()));
+    RET(snes_image_get_palette_map(im, map.data()));
+    std::string s;
+    s.reserve(NPIX * 3 + 16384);
+    char num[16];
+    s += "{\"palette\":[";
+    for (int p = 0; p < C; p++)
+        for (int i = 0; i < 16; i++) {
+            unsigned v = 0;
+            if (i != 0 && i <= S) {
+                const uint8_t *c = &pal[3 * (size_t)(p * S + i - 1)];
+                v = (unsigned)c[0] + ((unsigned)c[1] << 5) + ((unsigned)c[2] << 10);  // as_u16, lib.rs:679-681
+                v &= 0xffffu;
+            }
+            snprintf(num, sizeof num, "%u", v);
+            if (p || i) s += ',';
+            s += num;
+        }
+    s += "],\"tile_palettes\":[";
+    for (int t = 0; t < NTILES; t++) {
+        snprintf(num, sizeof num, "%u", (unsigned)tp[t]);
+        if (t) s += ',';
+        s += num;
+    }
+    s += "],\"tiles\":[";
+    for (int ty = 0; ty < 32; ty++)
+        for (int tx = 0; tx < 32; tx++) {
+            if (ty || tx) s += ',';
+            s += '[';
+            for (int y = 0; y < 8; y++)
+                for (int x = 0; x < 8; x++) {
+                    const int index = (ty * 8 + y) * W + tx * 8 + x;
+                    const unsigned v = im->alpha[index] == 0 ? 0u : (unsigned)map[index] + 1u;
+                    snprintf(num, sizeof num, "%u", v);
+                    if (y || x) s += ',';
+                    s += num;
+                }
+            s += ']';
+        }
+    s += "]}";
+    *len = s.size();
+    if (buf && cap > 0) {
+        const size_t n = s.size() < cap ? s.size() : cap;
+        memcpy(buf, s.data(), n);
+        if (s.size() < cap) buf[s.size()] = '\0';
+    }
+    return SNES_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched candidate evaluation
+// ------------------------------------------------------------------------------------------------
+static int check_slot(const snes_config &cfg, int palette, int index) {
+    if (palette < 0 || palette >= cfg.subpalette_count || index < 0 || index >= cfg.subpalette_size)
+        return fail(SNES_E_INVALID, "palette/index out of range");
+    return SNES_OK;
+}
+
+extern "C" int snes_batch_eval_candidates_dev(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
+                                              const uint8_t *d_cand, int ncand, int cand_idx_base, double *d_scores,
+                                              snes_best *d_best) {
+    RET(bind_images(ctx, images, nimg));
+    const snes_config cfg = images[0]->cfg;
+    RET(check_slot(cfg, palette, index));
+    if (!d_cand || ncand < 1) return fail(SNES_E_INVALID, "snes_batch_eval_candidates_dev: no candidates");
+    RET(ensure_evals(ctx, (size_t)nimg * ncand));
+    EvalPlan pl;
+    pl.nimg = nimg;
+    pl.ncand = ncand;
+    pl.ovr = palette * cfg.subpalette_size + index;
+    pl.d_cand = d_cand;
+    pl.do_assign = pl.do_score = true;
+    pl.d_scores = d_scores ? d_scores : ctx->scores;
+    RET(run_plan(ctx, cfg, pl));
+    if (d_best) {
+        k_argmin<<<nimg, 128, 0, ctx->stream>>>(pl.d_scores, ncand, cand_idx_base, reinterpret_cast<Best *>(d_best));
+        LAUNCHED(ctx);
+    }
+    return SNES_OK;
+}
+
+extern "C" int snes_batch_eval_candidates(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
+                                          const uint8_t *cand, int ncand, double *scores, uint8_t *maps, snes_best *best) {
+    RET(bind_images(ctx, images, nimg));
+    const snes_config cfg = images[0]->cfg;
+    RET(check_slot(cfg, palette, index));
+    if (!cand || ncand < 1) return fail(SNES_E_INVALID, "snes_batch_eval_candidates: no candidates");
+    const size_t E = (size_t)nimg * ncand;
+    for (size_t i = 0; i < E * 3; i++)
+        if (cand[i] > 32) return fail(SNES_E_INVALID, "snes_batch_eval_candidates: colour component > 32");
+    RET(ensure_evals(ctx, E));
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->cand, cand, E * 3, cudaMemcpyHostToDevice, st));
+    uint8_t *d_maps = nullptr;
+    if (maps) CK(cudaMalloc((void **)&d_maps, E * NPIX));
+    EvalPlan pl;
+    pl.nimg = nimg;
+    pl.ncand = ncand;
+    pl.ovr = palette * cfg.subpalette_size + index;
+    pl.d_cand = ctx->cand;
+    pl.do_assign = pl.do_score = true;
+    pl.d_maps_out = d_maps;
+    pl.d_scores = ctx->scores;
+    int rc = run_plan(ctx, cfg, pl);
+    if (rc == SNES_OK && best) {
+        k_argmin<<<nimg, 128, 0, st>>>(ctx->scores, ncand, 0, ctx->best);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = fail(SNES_E_CUDA, "k_argmin launch failed");
+    }
+    auto copy_out = [&]() -> int {
+        if (scores) CK(cudaMemcpyAsync(scores, ctx->scores, sizeof(double) * E, cudaMemcpyDeviceToHost, st));
+        if (best) CK(cudaMemcpyAsync(best, ctx->best, sizeof(Best) * nimg, cudaMemcpyDeviceToHost, st));
+        if (maps) CK(cudaMemcpyAsync(maps, d_maps, E * NPIX, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return SNES_OK;
+    };
+    if (rc == SNES_OK) rc = copy_out();
+    if (d_maps) cudaFree(d_maps);
+    return rc;
+}
+
+extern "C" int snes_batch_apply_best_dev(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
+                                         const uint8_t *d_cand_all, int ncand_all, const snes_best *d_best) {
+    RET(bind_images(ctx, images, nimg));
+    const snes_config cfg = images[0]->cfg;
+    RET(check_slot(cfg, palette, index));
+    if (!d_cand_all || !d_best || ncand_all < 1) return fail(SNES_E_INVALID, "snes_batch_apply_best_dev: NULL argument");
+    k_apply_best<<<(nimg + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_imgs, nimg, palette * cfg.subpalette_size + index, d_cand_all,
+                                                           ncand_all, reinterpret_cast<const Best *>(d_best), cfg.nes ? 1 : 0);
+    LAUNCHED(ctx);
+    return batch_optimize(ctx, images, nimg);  // lib.rs:236-237, 280-281, 324-325
+}
+
+// One optimize_palette_entry_* call for every image of the batch.
+//   mode 0: random (explicit candidates, lib.rs:191-240), 1: NES (lib.rs:242-284), 2: channel (lib.rs:286-328)
+static int batch_step(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index, int mode, int channel,
+                      const uint8_t *cand, int ncand, snes_best *best, double *errors_after) {
+    RET(bind_images(ctx, images, nimg));
+    const snes_config cfg = images[0]->cfg;
+    RET(check_slot(cfg, palette, index));
+    const int slot = palette * cfg.subpalette_size + index;
+    if (mode == 1) ncand = NES_COUNT;
+    if (mode == 2) ncand = 32;
+    if (mode == 2 && (channel < 0 || channel > 2)) return fail(SNES_E_INVALID, "channel out of range");
+    if (mode == 0 && (!cand || ncand < 1)) return fail(SNES_E_INVALID, "no candidates");
+    const size_t E = (size_t)nimg * ncand;
+    RET(ensure_evals(ctx, E));
+    cudaStream_t st = ctx->stream;
+    if (mode == 0) {
+        for (size_t i = 0; i < E * 3; i++)
+            if (cand[i] > 32) return fail(SNES_E_INVALID, "colour component > 32");
+        CK(cudaMemcpyAsync(ctx->cand, cand, E * 3, cudaMemcpyHostToDevice, st));
+    } else {
+        k_make_cands<<<nimg, 64, 0, st>>>(ctx->d_imgs, slot, mode == 1 ? -1 : channel, ctx->cand, ncand);
+        LAUNCHED(ctx);
+    }
+    if (mode != 1) RET(batch_error(ctx, images, nimg));  // best_error = self.error() (lib.rs:199, 294)
+    EvalPlan pl;
+    pl.nimg = nimg;
+    pl.ncand = ncand;
+    pl.ovr = slot;
+    pl.d_cand = ctx->cand;
+    pl.do_assign = pl.do_score = true;
+    pl.d_scores = ctx->scores;
+    RET(run_plan(ctx, cfg, pl));
+    k_argmin<<<nimg, 128, 0, st>>>(ctx->scores, ncand, 0, ctx->best);
+    LAUNCHED(ctx);
+    k_apply_best<<<(nimg + 127) / 128, 128, 0, st>>>(ctx->d_imgs, nimg, slot, ctx->cand, ncand, ctx->best, mode == 1);
+    LAUNCHED(ctx);
+    RET(batch_optimize(ctx, images, nimg));
+    if (best) CK(cudaMemcpyAsync(best, ctx->best, sizeof(Best) * nimg, cudaMemcpyDeviceToHost, st));
+    if (errors_after) {
+        RET(batch_error(ctx, images, nimg));
+        CK(cudaMemcpyAsync(errors_after, ctx->self_scores, sizeof(double) * nimg, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return SNES_OK;
+}
+
+extern "C" int snes_batch_step_random(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
+                                      const uint8_t *cand, int ncand, snes_best *best, double *errors_after) {
+    return batch_step(ctx, images, nimg, palette, index, 0, 0, cand, ncand, best, errors_after);
+}
+extern "C" int snes_batch_step_nes(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index, snes_best *best,
+                                   double *errors_after) {
+    return batch_step(ctx, images, nimg, palette, index, 1, 0, nullptr, 0, best, errors_after);
+}
+extern "C" int snes_batch_step_channel(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index, int channel,
+                                       snes_best *best, double *errors_after) {
+    return batch_step(ctx, images, nimg, palette, index, 2, channel, nullptr, 0, best, errors_after);
+}
+
+extern "C" int snes_image_optimize_palette_entry_random(snes_image *im, int palette, int index, const uint8_t *cand, int ncand) {
+    if (!im) return fail(SNES_E_INVALID, "image is NULL");
+    snes_image *one[1] = {im};
+    return batch_step(im->ctx, one, 1, palette, index, 0, 0, cand, ncand, nullptr, nullptr);
+}
+extern "C" int snes_image_optimize_palette_entry_nes(snes_image *im, int palette, int index) {
+    if (!im) return fail(SNES_E_INVALID, "image is NULL");
+    snes_image *one[1] = {im};
+    return batch_step(im->ctx, one, 1, palette, index, 1, 0, nullptr, 0, nullptr, nullptr);
+}
+extern "C" int snes_image_optimize_palette_entry_channel(snes_image *im, int palette, int index, int channel) {
+    if (!im) return fail(SNES_E_INVALID, "image is NULL");
+    snes_image *one[1] = {im};
+    return batch_step(im->ctx, one, 1, palette, index, 2, channel, nullptr, 0, nullptr, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// colour primitives for tests
+// ------------------------------------------------------------------------------------------------
+__global__ void k_closest(const uint8_t *colors5, int ncolors, const double *targets, int n, int cielab, const float4 *labtab,
+                          int32_t *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int t8[3];
+    for (int c = 0; c < 3; c++) {  // lib.rs:773-778
+        double v = targets[3 * i + c];
+        v = v < 0.0 ? 0.0 : (v > 255.0 ? 255.0 : v);
+        v = round(v);
+        t8[c] = (v != v) ? 0 : (int)v;
+    }
+    int bi = 0;
+    if (cielab) {
+        float tl, ta, tb;
+        srgb8_to_lab(t8[0], t8[1], t8[2], tl, ta, tb);
+        float best = __int_as_float(0x7f800000);
+        for (int j = 0; j < ncolors; j++) {
+            const float4 l = labtab[bgr555_index(colors5[3 * j], colors5[3 * j + 1], colors5[3 * j + 2])];
+            const float d = ciede2000(l.x, l.y, l.z, tl, ta, tb);
+            if (d < best) {
+                best = d;
+                bi = j;
+            }
+        }
+    } else {
+        int best = 0x7fffffff;
+        for (int j = 0; j < ncolors; j++) {
+            const uchar4 c = snes_as_rgba(colors5[3 * j], colors5[3 * j + 1], colors5[3 * j + 2]);
+            const int key = redmean_key(c.x, c.y, c.z, t8[0], t8[1], t8[2]);
+            if (key < best) {
+                best = key;
+                bi = j;
+            }
+        }
+    }
+    out[i] = bi;
+}
+
+__global__ void k_nes_only(const uint8_t *colors5, int n, int cielab, const float4 *labtab, uint8_t *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t o[3];
+    new_nes_only(colors5 + 3 * i, cielab, labtab, o);
+    out[3 * i] = o[0];
+    out[3 * i + 1] = o[1];
+    out[3 * i + 2] = o[2];
+}
+
+extern "C" int snes_closest_color_index(snes_ctx *ctx, const uint8_t *colors5, int ncolors, const double *targets, int n, int cielab,
+                                        int32_t *out_index) {
+    if (!ctx || !colors5 || !targets || !out_index || ncolors < 1 || n < 1) return fail(SNES_E_INVALID, "snes_closest_color_index: bad argument");
+    for (int i = 0; i < ncolors * 3; i++)
+        if (colors5[i] > 32) return fail(SNES_E_INVALID, "colour component > 32");
+    RET(set_device(ctx));
+    uint8_t *d_c = nullptr;
+    double *d_t = nullptr;
+    int32_t *d_o = nullptr;
+    cudaStream_t st = ctx->stream;
+    auto body = [&]() -> int {
+        CK(cudaMalloc((void **)&d_c, (size_t)ncolors * 3));
+        CK(cudaMalloc((void **)&d_t, sizeof(double) * 3 * n));
+        CK(cudaMalloc((void **)&d_o, sizeof(int32_t) * n));
+        CK(cudaMemcpyAsync(d_c, colors5, (size_t)ncolors * 3, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_t, targets, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
+        k_closest<<<(n + 127) / 128, 128, 0, st>>>(d_c, ncolors, d_t, n, cielab, ctx->labtab, d_o);
+        LAUNCHED(ctx);
+        CK(cudaMemcpyAsync(out_index, d_o, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return SNES_OK;
+    };
+    const int rc = body();
+    cudaFree(d_c);
+    cudaFree(d_t);
+    cudaFree(d_o);
+    return rc;
+}
+
+extern "C" int snes_new_nes_only(snes_ctx *ctx, const uint8_t *colors5, int n, int cielab, uint8_t *out5) {
+    if (!ctx || !colors5 || !out5 || n < 1) return fail(SNES_E_INVALID, "snes_new_nes_only: bad argument");
+    for (int i = 0; i < n * 3; i++)
+        if (colors5[i] > 32) return fail(SNES_E_INVALID, "colour component > 32");
+    RET(set_device(ctx));
+    uint8_t *d_c = nullptr, *d_o = nullptr;
+    cudaStream_t st = ctx->stream;
+    auto body = [&]() -> int {
+        CK(cudaMalloc((void **)&d_c, (size_t)n * 3));
+        CK(cudaMalloc((void **)&d_o, (size_t)n * 3));
+        CK(cudaMemcpyAsync(d_c, colors5, (size_t)n * 3, cudaMemcpyHostToDevice, st));
+        k_nes_only<<<(n + 127) / 128, 128, 0, st>>>(d_c, n, cielab, ctx->labtab, d_o);
+        LAUNCHED(ctx);
+        CK(cudaMemcpyAsync(out5, d_o, (size_t)n * 3, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return SNES_OK;
+    };
+    const int rc = body();
+    cudaFree(d_c);
+    cudaFree(d_o);
+    return rc;
+}
+
+extern "C" int snes_image_debug_planes(snes_image *im, float *xyb, float *mu1, float *s11) {
+    if (!im) return fail(SNES_E_INVALID, "image is NULL");
+    const size_t n = sizeof(float) * EVAL_XYB_FLOATS;
+    if (xyb) RET(d2h(im, xyb, im->dev.xyb_rm, n));
+    if (mu1) RET(d2h(im, mu1, im->dev.mu1, n));
+    if (s11) RET(d2h(im, s11, im->dev.s11, n));
+    return SNES_OK;
+}
+
+extern "C" int snes_image_debug_lab(snes_image *im, float *lab /* 65536*4 */) {
+    if (!im || !im->dev.lab) return fail(SNES_E_INVALID, "snes_image_debug_lab: image has no Lab plane (perceptual_palettes off)");
+    return d2h(im, lab, im->dev.lab, sizeof(float4) * NPIX);
+}
+
+extern "C" int snes_image_kmeans_debug(snes_image *im, double *centres /* 256*3 */, int32_t *status /* 512 */) {
+    if (!im || !im->km_slab) return fail(SNES_E_INVALID, "snes_image_kmeans_debug: no k-means has run on this image");
+    if (centres) RET(d2h(im, centres, im->km.centres, sizeof(double) * 3 * KM_MAXK));
+    if (status) RET(d2h(im, status, im->km.status, sizeof(int) * 512));
+    return SNES_OK;
+}

@@ -1,0 +1,318 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded
+inputs.  Integer/byte outputs (palette_map, tile_palettes, palette, JSON) must be bit-exact in RGB
+mode; SSIMULACRA2 errors must agree within SCORE_TOL; CIELAB choices within LAB_TOL."""
+import json
+
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from snesimage_b200 import engine, synth
+from util import lab_choice_ok, make_pair
+
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL = 1e-4   # north_star: |delta score| <= 1e-4; observed ~1e-11 (only f64 summation order differs)
+TIGHT_TOL = 1e-8
+LAB_TOL = 2e-4     # excess CIEDE2000 distance allowed for a differing CIELAB choice
+
+
+@pytest.mark.parametrize("family", ["V", "G", "B", "T"])
+def test_source_planes_bit_exact(ctx, family):
+    rgba = synth.image(3, family)
+    g, _ = make_pair(ctx, rgba, 2, 4)
+    xyb, mu1, s11 = g.debug_planes()
+    assert np.array_equal(xyb.view(np.uint32), ob.xyb_pyramid(rgba).view(np.uint32))
+    omu1, os11 = ob.source_planes(rgba)
+    assert np.array_equal(mu1.view(np.uint32), omu1.view(np.uint32))
+    assert np.array_equal(s11.view(np.uint32), os11.view(np.uint32))
+
+
+@pytest.mark.parametrize("family,C,S", [("V", 8, 15), ("G", 4, 7), ("B", 1, 7), ("T", 8, 15), ("V", 16, 16), ("T", 2, 1)])
+def test_optimize_rgb_bit_exact_and_error(ctx, family, C, S):
+    rgba = synth.image(11, family)
+    g, o = make_pair(ctx, rgba, C, S, seed=5)
+    g.optimize()
+    o.optimize()
+    assert np.array_equal(g.palette_map, o.palette_map)
+    assert np.array_equal(g.as_rgba(), o.as_rgba())
+    eg, eo = g.error(), o.error()
+    assert abs(eg - eo) <= TIGHT_TOL, (eg, eo)
+
+
+def test_error_identical_image_is_zero(ctx):
+    # an image made only of exact SNES colours, one subpalette holding them all: error() == 0.0
+    pal = synth.random_palette(2, 1, 15)
+    idx = (synth.hashn(7, 1, np.arange(65536)) % np.uint64(15)).astype(np.int64).reshape(256, 256)
+    rgb = np.stack([ob.snes_as_rgba(c)[:3] for c in pal])[idx]
+    rgba = np.concatenate([rgb, np.full((256, 256, 1), 255, np.uint8)], axis=2).astype(np.uint8)
+    g, o = make_pair(ctx, rgba, 1, 15, random_state=False)
+    g.palette = pal
+    o.palette = pal
+    g.optimize()
+    o.optimize()
+    assert np.array_equal(g.as_rgba(), rgba)
+    assert g.error() == 0.0 and o.error() == 0.0
+
+
+@pytest.mark.parametrize("family,C,S,dither", [("V", 8, 15, False), ("T", 4, 7, False), ("V", 8, 15, True), ("T", 4, 3, True)])
+def test_eval_candidates_rgb(ctx, family, C, S, dither):
+    rgba = synth.image(21, family)
+    g, o = make_pair(ctx, rgba, C, S, dither=dither, seed=8)
+    cand = synth.candidates(21, 0, 10)
+    cand[3] = o.palette[1 * S + 0]  # one candidate equal to the current entry
+    sg, mg = g.eval_candidates(1, 0, cand, want_maps=True)
+    so, mo = o.eval_candidates(1, 0, cand, want_maps=True)
+    assert np.array_equal(mg, mo)
+    assert np.max(np.abs(sg - so)) <= TIGHT_TOL, (sg, so)
+    # the batch call leaves the image's own state alone
+    assert np.array_equal(g.palette, o.palette)
+    r = engine.batch_eval_candidates([g], 1, 0, cand[None])
+    k = int(np.argmin(so))  # numpy argmin = first minimum = strict-< rule of lib.rs:216
+    assert r["best"]["idx"][0] == k and abs(r["best"]["err"][0] - so[k]) <= TIGHT_TOL
+
+
+@pytest.mark.parametrize("family,C,S", [("V", 8, 15), ("G", 2, 7), ("T", 4, 3), ("B", 1, 2)])
+def test_dither_rgb_bit_exact(ctx, family, C, S):
+    rgba = synth.image(31, family)
+    g, o = make_pair(ctx, rgba, C, S, dither=True, seed=9)
+    g.optimize()
+    o.optimize()
+    assert np.array_equal(g.palette_map, o.palette_map)
+    assert abs(g.error() - o.error()) <= TIGHT_TOL
+
+
+def test_dither_nes_bit_exact(ctx):
+    rgba = synth.image(32, "T")
+    g, o = make_pair(ctx, rgba, 4, 3, dither=True, nes=True, seed=10)
+    g.optimize()
+    o.optimize()
+    assert np.array_equal(g.palette_map, o.palette_map)
+
+
+def test_quirk_value_32_wraps(ctx):
+    # round(v/8) stores 32 for v >= 252 (lib.rs:396-400); as_rgba() then wraps to 8 (lib.rs:664)
+    rgba = synth.image(41, "V")
+    g, o = make_pair(ctx, rgba, 2, 4, seed=3)
+    pal = o.palette
+    pal[1] = (32, 5, 32)
+    pal[6] = (31, 32, 0)
+    for im in (g, o):
+        im.palette = pal
+        im.optimize()
+    assert np.array_equal(g.palette_map, o.palette_map)
+    assert np.array_equal(g.as_rgba(), o.as_rgba())
+    assert abs(g.error() - o.error()) <= TIGHT_TOL
+    assert g.as_json() == o.as_json()
+
+
+def test_closest_color_index_rgb(ctx):
+    rng = np.random.RandomState(5)
+    colors = rng.randint(0, 33, (15, 3)).astype(np.uint8)
+    t = rng.uniform(-40, 300, (4000, 3))
+    t[:500] = np.round(t[:500]) + 0.5          # exact halves: round half away from zero
+    t[500:600] = rng.randint(0, 256, (100, 3))  # exact integers
+    got = ctx.closest_color_index(colors, t, cielab=False)
+    want = np.array([ob.closest_color_index(colors, x, False) for x in t])
+    assert np.array_equal(got, want)
+
+
+def test_new_nes_only(ctx):
+    c5 = np.array([[r, g, b] for r in range(0, 33, 4) for g in range(0, 33, 4) for b in range(0, 33, 4)], np.uint8)
+    got = ctx.new_nes_only(c5, cielab=False)
+    want = np.stack([ob.new_nes_only(c, False) for c in c5])
+    assert np.array_equal(got, want)
+    got = ctx.new_nes_only(c5, cielab=True)
+    want = np.stack([ob.new_nes_only(c, True) for c in c5])
+    bad = np.argwhere((got != want).any(axis=1)).ravel()
+    for i in bad:  # a different NES colour is acceptable only if it is equally close for the oracle
+        rgba = ob.snes_as_rgba(c5[i])[:3]
+        dg = ob.cielab(rgba, ob.snes_as_rgba(got[i])[:3])
+        dw = ob.cielab(rgba, ob.snes_as_rgba(want[i])[:3])
+        assert dg - dw <= LAB_TOL
+    assert len(bad) <= len(c5) // 100
+
+
+# ---- CIELAB mode ---------------------------------------------------------------------------------
+def test_lab_planes_close(ctx):
+    rgba = synth.image(51, "V")
+    g, _ = make_pair(ctx, rgba, 4, 7, lab=True)
+    lab = g.debug_lab().reshape(256, 256, 3)
+    ys, xs = np.mgrid[0:256:7, 0:256:7]
+    want = np.stack([ob.srgb8_to_lab(*rgba[y, x, :3]) for y, x in zip(ys.ravel(), xs.ravel())])
+    got = lab[ys.ravel(), xs.ravel()]
+    # same f32 operation order; only cbrt differs (CUDA f64 cbrt rounded to f32 vs glibc cbrtf): a few ulp of
+    # f(t) ~ 0.8, scaled by 500 / 200 in a and b
+    assert np.max(np.abs(got - want)) <= 1e-4
+    assert np.mean(got.view(np.uint32) == want.view(np.uint32)) > 0.5
+
+
+@pytest.mark.parametrize("family,C,S,dither", [("V", 4, 7, False), ("T", 8, 15, False), ("G", 4, 7, True)])
+def test_optimize_lab_within_tolerance(ctx, family, C, S, dither):
+    rgba = synth.image(52, family)
+    g, o = make_pair(ctx, rgba, C, S, dither=dither, lab=True, seed=12)
+    g.optimize()
+    o.optimize()
+    gmap = g.palette_map
+    if not dither:
+        ndiff, worst = lab_choice_ok(o, gmap, LAB_TOL)
+        assert worst <= LAB_TOL, (ndiff, worst)
+        assert ndiff <= 65536 // 1000
+    else:
+        # error diffusion amplifies a single flipped choice; require near-total agreement
+        assert np.mean(gmap == o.palette_map) > 0.98
+    # scorer parity on the GPU's own choices
+    o.palette_map = gmap
+    assert abs(g.error() - o.error()) <= TIGHT_TOL
+
+
+# ---- k-means initialisation ------------------------------------------------------------------------
+@pytest.mark.parametrize("family,C,S", [("V", 8, 15), ("B", 4, 7), ("T", 8, 15), ("G", 1, 7)])
+def test_initialize_tiles_and_recalculate_rgb(ctx, family, C, S):
+    rgba = synth.image(61, family)
+    g, o = make_pair(ctx, rgba, C, S, random_state=False)
+    g.initialize_tiles()
+    o.initialize_tiles()
+    assert np.array_equal(g.tile_palettes, o.tile_palettes)
+    assert np.array_equal(g.palette, o.palette)
+    assert np.array_equal(g.palette_map, o.palette_map)
+    g.recalculate_palettes()
+    o.recalculate_palettes()
+    assert np.array_equal(g.palette, o.palette)
+    assert np.array_equal(g.palette_map, o.palette_map)
+    assert abs(g.error() - o.error()) <= TIGHT_TOL
+
+
+@pytest.mark.parametrize("nes", [False, True])
+def test_initialize_tiles_and_recalculate_lab(ctx, nes):
+    rgba = synth.image(62, "V")
+    g, o = make_pair(ctx, rgba, 4, 7, lab=True, nes=nes, random_state=False)
+    g.initialize_tiles()
+    o.initialize_tiles()
+    assert np.array_equal(g.tile_palettes, o.tile_palettes)
+    assert np.array_equal(g.palette, o.palette)
+    g.recalculate_palettes()
+    o.recalculate_palettes()
+    # Lab cluster sums are f64 sums of non-integers reduced in a different (fixed) order, and cbrt differs
+    # in the last ulp: allow one 5-bit step on a few entries
+    dp = np.abs(g.palette.astype(int) - o.palette.astype(int))
+    assert dp.max() <= (0 if not nes else 31)
+    assert (dp.sum(axis=1) > 0).sum() <= 1
+
+
+def test_kmeans_assertion_is_reported(ctx):
+    rgba = synth.image(63, "V").copy()
+    rgba[..., 3] = 0  # fully transparent: no points at all -> cogset would panic
+    g, o = make_pair(ctx, rgba, 4, 7, random_state=False)
+    with pytest.raises(engine.KmeansAssertion):
+        g.initialize_tiles()
+    with pytest.raises(RuntimeError):
+        o.initialize_tiles()
+
+
+# ---- palette-entry optimisers ------------------------------------------------------------------------
+def _start(ctx, rgba, C, S, **kw):
+    g, o = make_pair(ctx, rgba, C, S, random_state=False, **kw)
+    for im in (g, o):
+        im.initialize_tiles()
+        im.recalculate_palettes()
+    assert np.array_equal(g.palette, o.palette)
+    return g, o
+
+
+def test_optimize_palette_entry_random_and_channel(ctx):
+    rgba = synth.image(0, "V")
+    g, o = _start(ctx, rgba, 8, 15)
+    for it, (p, i) in enumerate([(0, 0), (0, 1), (3, 7)]):
+        cand = synth.candidates(0, it, 16)
+        g.optimize_palette_entry_random(p, i, cand)
+        o.optimize_palette_entry_random(p, i, cand)
+        assert np.array_equal(g.palette, o.palette)
+        assert np.array_equal(g.palette_map, o.palette_map)
+    for ch in range(3):
+        g.optimize_palette_entry_channel(2, 5, ch)
+        o.optimize_palette_entry_channel(2, 5, ch)
+        assert np.array_equal(g.palette, o.palette)
+    assert np.array_equal(g.palette_map, o.palette_map)
+    assert abs(g.error() - o.error()) <= TIGHT_TOL
+
+
+def test_optimize_palette_entry_nes_dither(ctx):
+    rgba = synth.image(4, "T")
+    g, o = _start(ctx, rgba, 4, 3, dither=True, nes=True)
+    for p, i in [(0, 0), (1, 2)]:
+        g.optimize_palette_entry_nes(p, i)
+        o.optimize_palette_entry_nes(p, i)
+        assert np.array_equal(g.palette, o.palette)
+        assert np.array_equal(g.palette_map, o.palette_map)
+
+
+def test_as_json_matches_reference_layout(ctx):
+    rgba = synth.image(71, "T")
+    g, o = make_pair(ctx, rgba, 8, 15, seed=4)
+    g.optimize()
+    o.optimize()
+    s = g.as_json_string()
+    doc = json.loads(s)
+    assert doc == o.as_json()
+    assert list(doc.keys()) == ["palette", "tile_palettes", "tiles"]  # serde_json Map = BTreeMap order
+    assert " " not in s and "\n" not in s                             # Value::to_string() is compact
+    assert len(doc["palette"]) == 16 * 8 and len(doc["tiles"]) == 1024 and len(doc["tile_palettes"]) == 1024
+    assert all(len(t) == 64 for t in doc["tiles"]) and max(max(t) for t in doc["tiles"]) <= 15
+
+
+# ---- batch / full-size properties (BASELINE.json configs[4]) --------------------------------------------
+def test_batch_properties_full_size(ctx):
+    C, S, nimg, ncand = 8, 15, 64, 64
+    cfg = engine.Config(subpalette_count=C, subpalette_size=S)
+    imgs = [engine.OptimizedImage(ctx, synth.image(s, "V"), cfg) for s in range(nimg)]
+    engine.batch_initialize_tiles(imgs)
+    engine.batch_recalculate_palettes(imgs)
+    errs = engine.batch_error(imgs)
+    cand = np.stack([synth.candidates(s, 0, ncand) for s in range(nimg)])
+    for j, im in enumerate(imgs):       # candidate 5 of every image = its current entry
+        cand[j, 5] = im.palette[2 * S + 3]
+    cand[:, 9] = cand[:, 8]             # duplicated candidate
+    r = engine.batch_eval_candidates(imgs, 2, 3, cand)
+    sc = r["scores"]
+    assert np.array_equal(sc[:, 5], errs)          # idempotence: unchanged palette -> the image's own error, bitwise
+    assert np.array_equal(sc[:, 9], sc[:, 8])      # determinism
+    assert np.array_equal(r["best"]["idx"], np.argmin(sc, axis=1))
+    assert np.array_equal(r["best"]["err"], sc[np.arange(nimg), np.argmin(sc, axis=1)])
+    # spot-check three (image, candidate) pairs against the oracle at full batch size
+    for j, k in [(0, 0), (17, 40), (63, 63)]:
+        o = ob.OracleImage(synth.image(j, "V"), C, S)
+        o.palette = imgs[j].palette
+        o.tile_palettes = imgs[j].tile_palettes
+        so = o.eval_candidates(2, 3, cand[j, k:k + 1])
+        assert abs(so[0] - sc[j, k]) <= TIGHT_TOL
+    # one whole optimiser step: the accepted colour is the argmin iff it beats the current error
+    best, after = engine.batch_step_random(imgs, 2, 3, cand, want_errors=True)
+    for j, im in enumerate(imgs):
+        k = int(np.argmin(sc[j]))
+        want = cand[j, k] if sc[j, k] < errs[j] else cand[j, 5]
+        assert np.array_equal(im.palette[2 * S + 3], want)
+        assert after[j] == min(sc[j, k], errs[j])
+    # chunking must not change anything
+    ctx.set_chunk(5)
+    r2 = engine.batch_eval_candidates(imgs[:3], 0, 0, cand[:3, :7])
+    ctx.set_chunk(16)
+    r3 = engine.batch_eval_candidates(imgs[:3], 0, 0, cand[:3, :7])
+    assert np.array_equal(r2["scores"], r3["scores"])
+    for im in imgs:
+        im.close()
+
+
+def test_invalid_arguments(ctx):
+    cfg = engine.Config(subpalette_count=2, subpalette_size=4)
+    with pytest.raises(engine.SnesGpuError):
+        engine.OptimizedImage(ctx, np.zeros((128, 256, 4), np.uint8), cfg)
+    with pytest.raises(engine.SnesGpuError):
+        engine.OptimizedImage(ctx, synth.image(0), engine.Config(subpalette_count=32, subpalette_size=16))
+    g = engine.OptimizedImage(ctx, synth.image(0), cfg)
+    with pytest.raises(engine.SnesGpuError):
+        g.optimize_palette_entry_random(2, 0, synth.candidates(0, 0, 4))
+    with pytest.raises(engine.SnesGpuError):
+        g.palette = np.full((8, 3), 40, np.uint8)
+    with pytest.raises(engine.SnesGpuError):
+        g.tile_palettes = np.full(1024, 2, np.uint8)
