@@ -65,10 +65,20 @@ int snes_ctx_create(int device, snes_ctx **out);
 void snes_ctx_destroy(snes_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t snes_ctx_kernel_launches(const snes_ctx *ctx);
-/* make the library enqueue on an external CUDA stream (e.g. torch's current stream); NULL = own stream */
+/* make the library enqueue on an external CUDA stream (e.g. torch's current stream); NULL = the context's own
+ * non-blocking stream; pass cudaStreamLegacy ((void*)0x1) to name the legacy default stream */
 int snes_ctx_set_stream(snes_ctx *ctx, void *cuda_stream);
 int snes_ctx_synchronize(snes_ctx *ctx);
-/* how many candidate evaluations have their intermediates live at once (default 16, env SNESGPU_CHUNK) */
+/* Per-launch device timing with CUDA events on the launching stream.  _begin clears and enables; _end
+ * disables, synchronises and writes a JSON object {"<kernel>": {"ms": total, "n": launches}, ...}
+ * (at most cap-1 bytes + NUL; *len = full length). */
+int snes_ctx_profile_begin(snes_ctx *ctx);
+int snes_ctx_profile_end(snes_ctx *ctx, char *buf, size_t cap, size_t *len);
+/* scorer selection: fused != 0 -> k_score_fused (blur planes stay in shared memory; default), 0 -> the
+ * multi-kernel pipeline that spills them to HBM (kept for A/B checks); block_width 16 or 32.
+ * Env overrides at context creation: SNESGPU_FUSED, SNESGPU_BW. */
+int snes_ctx_set_scorer(snes_ctx *ctx, int fused, int block_width);
+/* how many candidate evaluations have their scratch live at once (default 256, env SNESGPU_CHUNK) */
 int snes_ctx_set_chunk(snes_ctx *ctx, int evaluations);
 
 /* ---- OptimizedImage ------------------------------------------------------------------------- */
@@ -126,6 +136,9 @@ int snes_batch_eval_candidates_dev(snes_ctx *ctx, snes_image *const *images, int
  * per image (the full, unsharded list).  Asynchronous on the context's stream. */
 int snes_batch_apply_best_dev(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
                               const uint8_t *d_cand_all, int ncand_all, const snes_best *d_best);
+/* Cross-rank argmin after an all-gather of every rank's best[nimg]: d_gathered is [nranks][nimg] with global
+ * candidate indices; d_out[j] = lexicographic minimum of (err, idx) over ranks (lib.rs:216 for any rank count). */
+int snes_merge_best_dev(snes_ctx *ctx, const snes_best *d_gathered, int nranks, int nimg, snes_best *d_out);
 /* Host-buffer convenience for one whole optimiser step over many images (eval + argmin + accept). */
 int snes_batch_step_random(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
                            const uint8_t *cand /* nimg*ncand*3 */, int ncand, snes_best *best /* optional */,

@@ -21,6 +21,7 @@ constexpr int NSUMS = 6;                   // ssim d, d^4; edge artifact, artifa
 constexpr int PART_DOUBLES = NSCALES * 3 * NSEG * NSUMS;
 constexpr int MAX_ENTRIES = 256;           // sub_count * sub_size
 constexpr int BLACK = 256;                 // table slot of a transparent (rendered black) pixel
+constexpr int GI_BLACK = 255;              // transparent pixel in a gi-format scratch map (needs C*S <= 255)
 constexpr int NES_COUNT = 56;
 
 __host__ __device__ __forceinline__ int scale_off(int s) {  // pixel offset of scale s inside a pyramid
@@ -58,6 +59,7 @@ struct ImgDev {
     PalTables *tables;
     double *cur_err;          // error() of the current state
     const float *lab;         // per-pixel Lab of the original (perceptual mode), [NPIX][4]
+    const uint8_t *alpha;     // alpha channel of the original, [NPIX]
 };
 
 struct Best {

@@ -20,7 +20,7 @@ namespace snes {
 
 template <bool LAB>
 __global__ void __launch_bounds__(256) k_assign_dither(const ImgDev *imgs, const CandEntry *cents, int ncand, int e0, int S,
-                                                       int CS, int ovr, uint8_t *maps, int to_image) {
+                                                       int CS, int ovr, uint8_t *maps, int to_image, int gi_fmt) {
     __shared__ uchar4 pal[MAX_ENTRIES];
     __shared__ float4 pal_lab[LAB ? MAX_ENTRIES : 1];
     __shared__ double mail[2][H][3];
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) k_assign_dither(const ImgDev *imgs, const
             mail[t & 1][y][0] = ee[0];
             mail[t & 1][y][1] = ee[1];
             mail[t & 1][y][2] = ee[2];
-            packed |= (uint32_t)bi << (8 * (x & 3));
+            packed |= (uint32_t)(gi_fmt ? (p.w > 0 ? sub + bi : GI_BLACK) : bi) << (8 * (x & 3));
             if ((x & 3) == 3) {
                 *reinterpret_cast<uint32_t *>(out + (x & ~3)) = packed;
                 packed = 0;

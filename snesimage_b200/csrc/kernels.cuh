@@ -84,8 +84,10 @@ __global__ void __launch_bounds__(256) k_tables(const ImgDev *imgs, int nimg, in
 // grid = (64, E), block 256; each thread owns 4 horizontally adjacent pixels (one 16-byte load,
 // one 4-byte store).  to_image != 0 writes into the image's own palette_map (E == nimg).
 // ------------------------------------------------------------------------------------------------
+// gi_fmt != 0 (scratch maps of the fused scorer): each byte is the global entry index tile_sub*S + index, or
+// GI_BLACK for a transparent pixel, so the scorer needs neither tile_palettes nor alpha to render the pixel.
 __global__ void __launch_bounds__(256) k_assign_rgb(const ImgDev *imgs, const CandEntry *cents, int ncand, int e0, int S,
-                                                    int CS, int ovr, uint8_t *maps, int to_image) {
+                                                    int CS, int ovr, uint8_t *maps, int to_image, int gi_fmt) {
     __shared__ uchar4 pal[MAX_ENTRIES];
     const int e = blockIdx.y, ea = e0 + e, img = ea / ncand, tid = threadIdx.x;
     const ImgDev im = imgs[img];
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(256) k_assign_rgb(const ImgDev *imgs, const Ca
                 bi = j;
             }
         }
-        packed |= (uint32_t)(a > 0 ? bi : 0) << (8 * k);
+        packed |= (uint32_t)(gi_fmt ? (a > 0 ? sub + bi : GI_BLACK) : (a > 0 ? bi : 0)) << (8 * k);
     }
     uint8_t *out = to_image ? im.map : maps + (size_t)e * NPIX;
     reinterpret_cast<uint32_t *>(out)[q] = packed;
@@ -128,7 +130,8 @@ __global__ void __launch_bounds__(256) k_assign_rgb(const ImgDev *imgs, const Ca
 template <bool SRC>
 __global__ void __launch_bounds__(256) k_pyramid(const ImgDev *imgs, const CandEntry *cents, int ncand, int e0, int S,
                                                  int CS, int ovr, const uint8_t *maps, int from_image,
-                                                 float *xyb_rm_base, float *xyb_cm_base) {
+                                                 float *xyb_rm_base, float *xyb_cm_base, int lean, int gi_fmt) {
+    // lean != 0 (fused scorer): only the row-major planes of scales >= 1 are written
     __shared__ float s_lin[SRC ? 1 : MAX_ENTRIES + 1][3];
     __shared__ float s_xyb[SRC ? 1 : MAX_ENTRIES + 1][3];
     __shared__ float tile[3][32][33];
@@ -161,7 +164,8 @@ __global__ void __launch_bounds__(256) k_pyramid(const ImgDev *imgs, const CandE
         for (int k = 0; k < 4; k++) {
             const int dx = k & 1, dy = k >> 1;
             const int x = bx * 32 + 2 * qx + dx, y = by * 32 + 2 * qy + dy;
-            const uchar4 p = __ldg(im.rgba + y * W + x);
+            uchar4 p = make_uchar4(0, 0, 0, 0);
+            if (SRC || !gi_fmt) p = __ldg(im.rgba + y * W + x);
             float xv, yv, bv;
             if (SRC) {
                 lin[k][0] = c_lin_lut[p.x];
@@ -169,7 +173,13 @@ __global__ void __launch_bounds__(256) k_pyramid(const ImgDev *imgs, const CandE
                 lin[k][2] = c_lin_lut[p.z];
                 lin_to_pxyb(lin[k][0], lin[k][1], lin[k][2], xv, yv, bv);
             } else {
-                const int gi = p.w > 0 ? im.tile_pal[(y >> 3) * 32 + (x >> 3)] * S + map[y * W + x] : BLACK;
+                int gi;
+                if (gi_fmt) {
+                    gi = map[y * W + x];
+                    gi = gi == GI_BLACK ? BLACK : gi;
+                } else {
+                    gi = p.w > 0 ? im.tile_pal[(y >> 3) * 32 + (x >> 3)] * S + map[y * W + x] : BLACK;
+                }
                 lin[k][0] = s_lin[gi][0];
                 lin[k][1] = s_lin[gi][1];
                 lin[k][2] = s_lin[gi][2];
@@ -183,12 +193,13 @@ __global__ void __launch_bounds__(256) k_pyramid(const ImgDev *imgs, const CandE
         }
         __syncthreads();
         // scale 0 out: 128-byte rows in both layouts
-        for (int r = warp; r < 32; r += 8)
+        if (!lean)
+            for (int r = warp; r < 32; r += 8)
 #pragma unroll
-            for (int c = 0; c < 3; c++) {
-                rm[c * NPIX + (by * 32 + r) * W + bx * 32 + lane] = tile[c][r][lane];
-                cm[c * NPIX + (bx * 32 + r) * H + by * 32 + lane] = tile[c][lane][r];
-            }
+                for (int c = 0; c < 3; c++) {
+                    rm[c * NPIX + (by * 32 + r) * W + bx * 32 + lane] = tile[c][r][lane];
+                    cm[c * NPIX + (bx * 32 + r) * H + by * 32 + lane] = tile[c][lane][r];
+                }
         // scales 1..5: m x m pixels of this region, m = 16, 8, 4, 2, 1
         float cur[3];
 #pragma unroll
@@ -225,7 +236,7 @@ __global__ void __launch_bounds__(256) k_pyramid(const ImgDev *imgs, const CandE
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
                     rm[off + (size_t)c * d * d + (by * m + ay) * d + bx * m + ax] = tile[c][ay][ax];
-                    cm[off + (size_t)c * d * d + (bx * m + ay) * d + by * m + ax] = tile[c][ax][ay];
+                    if (!lean) cm[off + (size_t)c * d * d + (bx * m + ay) * d + by * m + ax] = tile[c][ax][ay];
                 }
             }
         }
@@ -516,6 +527,20 @@ __global__ void __launch_bounds__(128) k_argmin(const double *scores, int ncand,
         b.pad = 0;
         best[img] = b;
     }
+}
+
+// k_merge_best: the cross-rank argmin after the all-gather: gathered[r][j] is rank r's (error, index)
+// for image j, with indices already global; the lexicographic minimum reproduces the strict-< /
+// lowest-index-wins rule of lib.rs:216 for any number of ranks.  One thread per image.
+__global__ void k_merge_best(const Best *gathered, int nranks, int nimg, Best *out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nimg) return;
+    Best b = gathered[j];
+    for (int r = 1; r < nranks; r++) {
+        const Best o = gathered[(size_t)r * nimg + j];
+        if (o.idx >= 0 && (b.idx < 0 || best_less(o.err, o.idx, b.err, b.idx))) b = o;
+    }
+    out[j] = b;
 }
 
 // ------------------------------------------------------------------------------------------------

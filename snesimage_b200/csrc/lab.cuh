@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256) k_image_lab(const uchar4 *rgba, float4 *l
 // k_assign_lab: optimize() (lib.rs:425-501) without dithering, CIEDE2000 metric.  Same launch shape
 // and outputs as k_assign_rgb: grid (64, E), block 256, 4 pixels per thread.
 __global__ void __launch_bounds__(256) k_assign_lab(const ImgDev *imgs, const CandEntry *cents, int ncand, int e0, int S,
-                                                    int CS, int ovr, uint8_t *maps, int to_image) {
+                                                    int CS, int ovr, uint8_t *maps, int to_image, int gi_fmt) {
     __shared__ float4 pal[MAX_ENTRIES];
     const int e = blockIdx.y, ea = e0 + e, img = ea / ncand, tid = threadIdx.x;
     const ImgDev im = imgs[img];
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256) k_assign_lab(const ImgDev *imgs, const Ca
                 bi = j;
             }
         }
-        packed |= (uint32_t)(a > 0 ? bi : 0) << (8 * k);
+        packed |= (uint32_t)(gi_fmt ? (a > 0 ? sub + bi : GI_BLACK) : (a > 0 ? bi : 0)) << (8 * k);
     }
     uint8_t *out = to_image ? im.map : maps + (size_t)e * NPIX;
     reinterpret_cast<uint32_t *>(out)[q] = packed;

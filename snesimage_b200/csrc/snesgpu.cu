@@ -17,6 +17,7 @@
 #include "kernels.cuh"
 #include "kmeans.cuh"
 #include "lab.cuh"
+#include "score_fused.cuh"
 
 using namespace snes;
 
@@ -52,7 +53,9 @@ struct snes_ctx {
     int device = 0;
     cudaStream_t own = nullptr, stream = nullptr;
     int64_t launches = 0;
-    int chunk = 16;  // evaluations whose intermediates are live at once (sized to stay L2-resident)
+    int chunk = 256;  // evaluations whose scratch (palette_map, coarse XYB pyramid) is live at once
+    int fused = 1;    // 1: k_score_fused (on-chip blur planes); 0: multi-kernel pipeline (SNESGPU_FUSED=0)
+    int bw = 32;      // column-block width of the fused scorer (16 or 32, SNESGPU_BW)
 
     // per-chunk scratch
     size_t chunk_cap = 0;
@@ -71,6 +74,12 @@ struct snes_ctx {
     std::vector<snes_image *> cached;
 
     float4 *labtab = nullptr;  // BGR555 -> Lab<D65,f32>
+
+    // per-launch CUDA-event timing (snes_ctx_profile_begin/end)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;
+    std::vector<const char *> prof_names;
+    size_t prof_used = 0;
 };
 
 struct snes_image {
@@ -81,6 +90,35 @@ struct snes_image {
     void *slab = nullptr, *km_slab = nullptr;
     std::vector<uint8_t> alpha;  // host copy of the alpha channel (as_json)
 };
+
+static void prof_begin(snes_ctx *ctx, const char *name) {
+    if (!ctx->profiling) return;
+    if (ctx->prof_used + 2 > ctx->prof_events.size()) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        ctx->prof_events.push_back(a);
+        ctx->prof_events.push_back(b);
+    }
+    ctx->prof_names.push_back(name);
+    cudaEventRecord(ctx->prof_events[ctx->prof_used], ctx->stream);
+}
+static void prof_end(snes_ctx *ctx) {
+    if (!ctx->profiling) return;
+    cudaEventRecord(ctx->prof_events[ctx->prof_used + 1], ctx->stream);
+    ctx->prof_used += 2;
+}
+
+// Every kernel launch goes through LAUNCH: it counts the launch and, while profiling is on, brackets it
+// with CUDA events on the launching stream (per-kernel device time for bench.py's roofline object).
+#define LAUNCH(ctx, name, ...)          \
+    do {                                \
+        prof_begin((ctx), (name));      \
+        __VA_ARGS__;                    \
+        prof_end((ctx));                \
+        (ctx)->launches++;              \
+        CK(cudaGetLastError());         \
+    } while (0)
 
 static int set_device(snes_ctx *ctx) {
     CK(cudaSetDevice(ctx->device));
@@ -185,6 +223,9 @@ extern "C" int snes_ctx_create(int device, snes_ctx **out) {
         if (v > 0) ctx->chunk = v;
     }
 
+    if (const char *c = getenv("SNESGPU_FUSED")) ctx->fused = atoi(c) != 0;
+    if (const char *c = getenv("SNESGPU_BW")) ctx->bw = atoi(c) == 16 ? 16 : 32;
+
     float lut[256], lut2[256], n2[3], d1[3];
     for (int v = 0; v < 256; v++) {
         lut[v] = srgb_eotf_yuvxyb((float)v / 255.0f);
@@ -207,11 +248,11 @@ extern "C" int snes_ctx_create(int device, snes_ctx **out) {
     CK(cudaMemcpyToSymbol(c_nes, nes4, sizeof(nes4)));
     CK(cudaFuncSetAttribute(k_blur_h<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlurHSmem0));
     CK(cudaFuncSetAttribute(k_blur_h<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlurHSmem1));
+    CK(cudaFuncSetAttribute(k_score_fused<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<32>)));
+    CK(cudaFuncSetAttribute(k_score_fused<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<16>)));
 
     RET(dev_alloc(&ctx->labtab, 32768));
-    k_build_lab_table<<<128, 256, 0, ctx->stream>>>(ctx->labtab);
-    ctx->launches++;
-    CK(cudaGetLastError());
+    LAUNCH(ctx, "k_build_lab_table", k_build_lab_table<<<128, 256, 0, ctx->stream>>>(ctx->labtab));
     CK(cudaStreamSynchronize(ctx->stream));
     *out = ctx;
     return SNES_OK;
@@ -238,6 +279,7 @@ extern "C" void snes_ctx_destroy(snes_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     free_scratch(ctx);
     cudaFree(ctx->labtab);
+    for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->own);
     delete ctx;
 }
@@ -256,6 +298,61 @@ extern "C" int snes_ctx_synchronize(snes_ctx *ctx) {
     if (!ctx) return fail(SNES_E_INVALID, "ctx is NULL");
     RET(set_device(ctx));
     CK(cudaStreamSynchronize(ctx->stream));
+    return SNES_OK;
+}
+
+extern "C" int snes_ctx_profile_begin(snes_ctx *ctx) {
+    if (!ctx) return fail(SNES_E_INVALID, "ctx is NULL");
+    ctx->profiling = true;
+    ctx->prof_names.clear();
+    ctx->prof_used = 0;
+    return SNES_OK;
+}
+
+// Stops profiling, drains the stream and writes {"kernel": {"ms": total, "n": launches}, ...} as JSON.
+extern "C" int snes_ctx_profile_end(snes_ctx *ctx, char *buf, size_t cap, size_t *len) {
+    if (!ctx || !len) return fail(SNES_E_INVALID, "snes_ctx_profile_end: NULL argument");
+    RET(set_device(ctx));
+    ctx->profiling = false;
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<std::string> names;
+    std::vector<double> ms;
+    std::vector<long> cnt;
+    for (size_t i = 0; i < ctx->prof_names.size(); i++) {
+        float t = 0.0f;
+        CK(cudaEventElapsedTime(&t, ctx->prof_events[2 * i], ctx->prof_events[2 * i + 1]));
+        size_t k = 0;
+        while (k < names.size() && names[k] != ctx->prof_names[i]) k++;
+        if (k == names.size()) {
+            names.push_back(ctx->prof_names[i]);
+            ms.push_back(0.0);
+            cnt.push_back(0);
+        }
+        ms[k] += t;
+        cnt[k]++;
+    }
+    std::string s = "{";
+    char tmp[128];
+    for (size_t k = 0; k < names.size(); k++) {
+        snprintf(tmp, sizeof tmp, "%s\"%s\": {\"ms\": %.6f, \"n\": %ld}", k ? ", " : "", names[k].c_str(), ms[k], cnt[k]);
+        s += tmp;
+    }
+    s += "}";
+    ctx->prof_names.clear();
+    ctx->prof_used = 0;
+    *len = s.size();
+    if (buf && cap > 0) {
+        const size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
+        memcpy(buf, s.data(), n);
+        buf[n] = '\0';
+    }
+    return SNES_OK;
+}
+
+extern "C" int snes_ctx_set_scorer(snes_ctx *ctx, int fused, int block_width) {
+    if (!ctx || (block_width != 16 && block_width != 32)) return fail(SNES_E_INVALID, "snes_ctx_set_scorer: bad argument");
+    ctx->fused = fused != 0;
+    ctx->bw = block_width;
     return SNES_OK;
 }
 
@@ -343,11 +440,6 @@ static int bind_images(snes_ctx *ctx, snes_image *const *images, int nimg) {
     return SNES_OK;
 }
 
-#define LAUNCHED(ctx)               \
-    do {                            \
-        (ctx)->launches++;          \
-        CK(cudaGetLastError());     \
-    } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // the evaluation pipeline
@@ -373,42 +465,61 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
     if (pl.do_score || (pl.do_assign && !pl.self && !pl.d_maps_out)) RET(ensure_chunk(ctx, (size_t)chunk));
     const float4 *labtab = cfg.perceptual_palettes ? ctx->labtab : nullptr;
 
-    k_tables<<<pl.nimg + (pl.ovr >= 0 ? (E + 255) / 256 : 0), 256, 0, st>>>(ctx->d_imgs, pl.nimg, CS, pl.d_cand,
-                                                                          pl.ovr >= 0 ? E : 0, ctx->cents, labtab);
-    LAUNCHED(ctx);
+    LAUNCH(ctx, "k_tables", k_tables<<<pl.nimg + (pl.ovr >= 0 ? (E + 255) / 256 : 0), 256, 0, st>>>(ctx->d_imgs, pl.nimg, CS, pl.d_cand,
+                                                                          pl.ovr >= 0 ? E : 0, ctx->cents, labtab));
 
     for (int e0 = 0; e0 < E; e0 += chunk) {
         const int ec = E - e0 < chunk ? E - e0 : chunk;
         uint8_t *maps = pl.d_maps_out ? pl.d_maps_out + (size_t)e0 * NPIX : ctx->maps;
+        // scratch maps feed only the fused scorer: write global entry indices (no tile_palettes / alpha lookups later)
+        const int gi = (ctx->fused && pl.do_score && !pl.self && !pl.d_maps_out && CS <= 255) ? 1 : 0;
         if (pl.do_assign) {
-            if (cfg.dither) {
-                if (cfg.perceptual_palettes)
-                    k_assign_dither<true><<<ec, 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self);
-                else
-                    k_assign_dither<false><<<ec, 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self);
+            if (cfg.dither && cfg.perceptual_palettes) {
+                LAUNCH(ctx, "k_assign_dither<true>", k_assign_dither<true><<<ec, 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self, gi));
+            } else if (cfg.dither) {
+                LAUNCH(ctx, "k_assign_dither<false>", k_assign_dither<false><<<ec, 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self, gi));
             } else if (cfg.perceptual_palettes) {
-                k_assign_lab<<<dim3(64, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self);
+                LAUNCH(ctx, "k_assign_lab", k_assign_lab<<<dim3(64, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self, gi));
             } else {
-                k_assign_rgb<<<dim3(64, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self);
+                LAUNCH(ctx, "k_assign_rgb", k_assign_rgb<<<dim3(64, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self, gi));
             }
-            LAUNCHED(ctx);
         }
         if (!pl.do_score) continue;
-        k_pyramid<false><<<dim3(16, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self,
-                                                       ctx->xyb_rm, ctx->xyb_cm);
-        LAUNCHED(ctx);
+        if (ctx->fused) {
+            LAUNCH(ctx, "k_pyramid<false>", k_pyramid<false><<<dim3(16, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self,
+                                                       ctx->xyb_rm, ctx->xyb_cm, 1, gi));
+            FusedArgs fa;
+            fa.imgs = ctx->d_imgs;
+            fa.cents = ctx->cents;
+            fa.ncand = pl.ncand;
+            fa.e0 = e0;
+            fa.S = S;
+            fa.CS = CS;
+            fa.ovr = pl.ovr;
+            fa.maps = maps;
+            fa.from_image = pl.self;
+            fa.gi_fmt = gi;
+            fa.xyb_rm = ctx->xyb_rm;
+            fa.partials = ctx->partials;
+            if (ctx->bw == 16)
+                LAUNCH(ctx, "k_score_fused<16>", k_score_fused<16><<<dim3(3, ec), FUSED_THREADS, sizeof(FusedSmem<16>), st>>>(fa));
+            else
+                LAUNCH(ctx, "k_score_fused<32>", k_score_fused<32><<<dim3(3, ec), FUSED_THREADS, sizeof(FusedSmem<32>), st>>>(fa));
+            continue;
+        }
+        LAUNCH(ctx, "k_pyramid<false>", k_pyramid<false><<<dim3(16, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self,
+                                                       ctx->xyb_rm, ctx->xyb_cm, 0, 0));
         for (int s = 0; s < NSCALES; s++) {
             const int d = W >> s, lines = ec * 3 * d;
-            k_blur_h<0><<<(lines + 127) / 128, 128, kBlurHSmem0, st>>>(s, lines, ctx->d_imgs, pl.ncand, e0, ctx->xyb_cm, ctx->hbuf);
-            LAUNCHED(ctx);
-            k_blur_v<0><<<(lines + 127) / 128, 128, 0, st>>>(s, lines, ctx->d_imgs, pl.ncand, e0, ctx->xyb_rm, ctx->hbuf,
-                                                           ctx->partials);
-            LAUNCHED(ctx);
+            LAUNCH(ctx, "k_blur_h<0>", k_blur_h<0><<<(lines + 127) / 128, 128, kBlurHSmem0, st>>>(s, lines, ctx->d_imgs, pl.ncand, e0, ctx->xyb_cm, ctx->hbuf));
+            LAUNCH(ctx, "k_blur_v<0>", k_blur_v<0><<<(lines + 127) / 128, 128, 0, st>>>(s, lines, ctx->d_imgs, pl.ncand, e0, ctx->xyb_rm, ctx->hbuf,
+                                                           ctx->partials));
         }
     }
-    if (pl.do_score) {
-        k_pool<<<(E + 127) / 128, 128, 0, st>>>(ctx->partials, E, pl.d_scores);
-        LAUNCHED(ctx);
+    if (pl.do_score && ctx->fused) {
+        LAUNCH(ctx, "k_pool_fused", k_pool_fused<<<(E + 127) / 128, 128, 0, st>>>(ctx->partials, E, pl.d_scores));
+    } else if (pl.do_score) {
+        LAUNCH(ctx, "k_pool", k_pool<<<(E + 127) / 128, 128, 0, st>>>(ctx->partials, E, pl.d_scores));
     }
     return SNES_OK;
 }
@@ -432,8 +543,7 @@ static int batch_error(snes_ctx *ctx, snes_image *const *images, int nimg) {
     pl.do_score = true;
     pl.d_scores = ctx->self_scores;
     RET(run_plan(ctx, images[0]->cfg, pl));
-    k_store_cur_err<<<(nimg + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_imgs, nimg, ctx->self_scores);
-    LAUNCHED(ctx);
+    LAUNCH(ctx, "k_store_cur_err", k_store_cur_err<<<(nimg + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_imgs, nimg, ctx->self_scores));
     return SNES_OK;
 }
 
@@ -473,6 +583,7 @@ extern "C" int snes_image_new(snes_ctx *ctx, const uint8_t *rgba, int width, int
     const size_t o_rm = take(plane), o_cm = take(plane), o_mu = take(plane), o_s11 = take(plane);
     const size_t o_tab = take(sizeof(PalTables)), o_err = take(sizeof(double));
     const size_t o_lab = take(im->cfg.perceptual_palettes ? sizeof(float4) * NPIX : 0);
+    const size_t o_alpha = take(NPIX);
     cudaError_t e = cudaMalloc(&im->slab, off);
     if (e != cudaSuccess) {
         delete im;
@@ -490,6 +601,7 @@ extern "C" int snes_image_new(snes_ctx *ctx, const uint8_t *rgba, int width, int
     im->dev.tables = (PalTables *)(b + o_tab);
     im->dev.cur_err = (double *)(b + o_err);
     im->dev.lab = im->cfg.perceptual_palettes ? (const float *)(b + o_lab) : nullptr;
+    im->dev.alpha = (const uint8_t *)(b + o_alpha);
 
     cudaStream_t st = ctx->stream;
     int rc = SNES_OK;
@@ -498,22 +610,19 @@ extern "C" int snes_image_new(snes_ctx *ctx, const uint8_t *rgba, int width, int
         CK(cudaMemsetAsync(b + o_tab, 0, sizeof(PalTables), st));
         CK(cudaMemsetAsync(b + o_err, 0, sizeof(double), st));
         CK(cudaMemcpyAsync(b + o_rgba, rgba, NPIX * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b + o_alpha, im->alpha.data(), NPIX, cudaMemcpyHostToDevice, st));
         if (im->cfg.perceptual_palettes) {
-            k_image_lab<<<256, 256, 0, st>>>(im->dev.rgba, (float4 *)(b + o_lab));
-            LAUNCHED(ctx);
+            LAUNCH(ctx, "k_image_lab", k_image_lab<<<256, 256, 0, st>>>(im->dev.rgba, (float4 *)(b + o_lab)));
         }
         // source side of SSIMULACRA2, once per image: XYB pyramid, mu1 = blur(i1), s11 = blur(i1*i1)
         snes_image *one[1] = {im};
         RET(bind_images(ctx, one, 1));
         RET(ensure_chunk(ctx, 1));
-        k_pyramid<true><<<dim3(16, 1), 256, 0, st>>>(ctx->d_imgs, nullptr, 1, 0, 0, 0, -1, nullptr, 0, nullptr, nullptr);
-        LAUNCHED(ctx);
+        LAUNCH(ctx, "k_pyramid<true>", k_pyramid<true><<<dim3(16, 1), 256, 0, st>>>(ctx->d_imgs, nullptr, 1, 0, 0, 0, -1, nullptr, 0, nullptr, nullptr, 0, 0));
         for (int s = 0; s < NSCALES; s++) {
             const int d = W >> s, lines = 3 * d;
-            k_blur_h<1><<<(lines + 127) / 128, 128, kBlurHSmem1, st>>>(s, lines, ctx->d_imgs, 1, 0, nullptr, ctx->hbuf);
-            LAUNCHED(ctx);
-            k_blur_v<1><<<(lines + 127) / 128, 128, 0, st>>>(s, lines, ctx->d_imgs, 1, 0, nullptr, ctx->hbuf, nullptr);
-            LAUNCHED(ctx);
+            LAUNCH(ctx, "k_blur_h<1>", k_blur_h<1><<<(lines + 127) / 128, 128, kBlurHSmem1, st>>>(s, lines, ctx->d_imgs, 1, 0, nullptr, ctx->hbuf));
+            LAUNCH(ctx, "k_blur_v<1>", k_blur_v<1><<<(lines + 127) / 128, 128, 0, st>>>(s, lines, ctx->d_imgs, 1, 0, nullptr, ctx->hbuf, nullptr));
         }
         CK(cudaStreamSynchronize(st));
         return SNES_OK;
@@ -580,14 +689,11 @@ static int batch_recalc(snes_ctx *ctx, snes_image *const *images, int nimg, int 
     const snes_config cfg = images[0]->cfg;
     const int C = only_sub0 ? 1 : cfg.subpalette_count, S = cfg.subpalette_size;
     cudaStream_t st = ctx->stream;
-    k_gather_points<<<nimg, 1024, 0, st>>>(ctx->d_imgs, ctx->d_km, cfg.subpalette_count, cfg.perceptual_palettes);
-    LAUNCHED(ctx);
+    LAUNCH(ctx, "k_gather_points", k_gather_points<<<nimg, 1024, 0, st>>>(ctx->d_imgs, ctx->d_km, cfg.subpalette_count, cfg.perceptual_palettes));
     for (int j = 0; j < nimg; j++) CK(cudaMemsetAsync(images[j]->km.status, 0xff, sizeof(int) * 2 * 256, st));
     // grid is (image, subpalette) with C as the stride; with only_sub0 the grid covers subpalette 0 only
-    k_kmeans<false><<<nimg * C, 1024, 0, st>>>(ctx->d_imgs, ctx->d_km, C, S);
-    LAUNCHED(ctx);
-    k_centres_to_palette<<<nimg, 256, 0, st>>>(ctx->d_imgs, ctx->d_km, C, S, cfg.perceptual_palettes, cfg.nes, ctx->labtab, 0);
-    LAUNCHED(ctx);
+    LAUNCH(ctx, "k_kmeans<false>", k_kmeans<false><<<nimg * C, 1024, 0, st>>>(ctx->d_imgs, ctx->d_km, C, S));
+    LAUNCH(ctx, "k_centres_to_palette", k_centres_to_palette<<<nimg, 256, 0, st>>>(ctx->d_imgs, ctx->d_km, C, S, cfg.perceptual_palettes, cfg.nes, ctx->labtab, 0));
     std::vector<int> status(C);
     for (int j = 0; j < nimg; j++) {
         CK(cudaMemcpyAsync(status.data(), images[j]->km.status, sizeof(int) * C, cudaMemcpyDeviceToHost, st));
@@ -615,14 +721,11 @@ extern "C" int snes_batch_initialize_tiles(snes_ctx *ctx, snes_image *const *ima
     if (cfg.subpalette_count == 1) {  // lib.rs:80-84
         RET(batch_recalc(ctx, images, nimg, 1));
     } else {
-        k_tile_means<<<nimg, 1024, 0, st>>>(ctx->d_imgs, ctx->d_km, cfg.perceptual_palettes);
-        LAUNCHED(ctx);
+        LAUNCH(ctx, "k_tile_means", k_tile_means<<<nimg, 1024, 0, st>>>(ctx->d_imgs, ctx->d_km, cfg.perceptual_palettes));
         for (int j = 0; j < nimg; j++) CK(cudaMemsetAsync(images[j]->km.status, 0xff, sizeof(int) * 2 * 256, st));
-        k_kmeans<true><<<nimg, 1024, 0, st>>>(ctx->d_imgs, ctx->d_km, cfg.subpalette_count, cfg.subpalette_count);
-        LAUNCHED(ctx);
-        k_centres_to_palette<<<nimg, 256, 0, st>>>(ctx->d_imgs, ctx->d_km, cfg.subpalette_count, cfg.subpalette_size,
-                                                  cfg.perceptual_palettes, cfg.nes, ctx->labtab, 1);
-        LAUNCHED(ctx);
+        LAUNCH(ctx, "k_kmeans<true>", k_kmeans<true><<<nimg, 1024, 0, st>>>(ctx->d_imgs, ctx->d_km, cfg.subpalette_count, cfg.subpalette_count));
+        LAUNCH(ctx, "k_centres_to_palette", k_centres_to_palette<<<nimg, 256, 0, st>>>(ctx->d_imgs, ctx->d_km, cfg.subpalette_count, cfg.subpalette_size,
+                                                  cfg.perceptual_palettes, cfg.nes, ctx->labtab, 1));
         for (int j = 0; j < nimg; j++) {
             int status = -1;
             CK(cudaMemcpyAsync(&status, images[j]->km.status, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -684,8 +787,7 @@ extern "C" int snes_image_as_rgba(snes_image *im, uint8_t *out_rgba) {
     RET(set_device(ctx));
     RET(ensure_chunk(ctx, 1));
     uchar4 *tmp = reinterpret_cast<uchar4 *>(ctx->hbuf);
-    k_as_rgba<<<256, 256, 0, ctx->stream>>>(im->dev, im->cfg.subpalette_size, tmp);
-    LAUNCHED(ctx);
+    LAUNCH(ctx, "k_as_rgba", k_as_rgba<<<256, 256, 0, ctx->stream>>>(im->dev, im->cfg.subpalette_size, tmp));
     CK(cudaMemcpyAsync(out_rgba, tmp, NPIX * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return SNES_OK;
@@ -814,8 +916,7 @@ extern "C" int snes_batch_eval_candidates_dev(snes_ctx *ctx, snes_image *const *
     pl.d_scores = d_scores ? d_scores : ctx->scores;
     RET(run_plan(ctx, cfg, pl));
     if (d_best) {
-        k_argmin<<<nimg, 128, 0, ctx->stream>>>(pl.d_scores, ncand, cand_idx_base, reinterpret_cast<Best *>(d_best));
-        LAUNCHED(ctx);
+        LAUNCH(ctx, "k_argmin", k_argmin<<<nimg, 128, 0, ctx->stream>>>(pl.d_scores, ncand, cand_idx_base, reinterpret_cast<Best *>(d_best)));
     }
     return SNES_OK;
 }
@@ -844,9 +945,10 @@ extern "C" int snes_batch_eval_candidates(snes_ctx *ctx, snes_image *const *imag
     pl.d_scores = ctx->scores;
     int rc = run_plan(ctx, cfg, pl);
     if (rc == SNES_OK && best) {
-        k_argmin<<<nimg, 128, 0, st>>>(ctx->scores, ncand, 0, ctx->best);
-        ctx->launches++;
-        if (cudaGetLastError() != cudaSuccess) rc = fail(SNES_E_CUDA, "k_argmin launch failed");
+        rc = [&]() -> int {
+            LAUNCH(ctx, "k_argmin", k_argmin<<<nimg, 128, 0, st>>>(ctx->scores, ncand, 0, ctx->best));
+            return SNES_OK;
+        }();
     }
     auto copy_out = [&]() -> int {
         if (scores) CK(cudaMemcpyAsync(scores, ctx->scores, sizeof(double) * E, cudaMemcpyDeviceToHost, st));
@@ -860,15 +962,22 @@ extern "C" int snes_batch_eval_candidates(snes_ctx *ctx, snes_image *const *imag
     return rc;
 }
 
+extern "C" int snes_merge_best_dev(snes_ctx *ctx, const snes_best *d_gathered, int nranks, int nimg, snes_best *d_out) {
+    if (!ctx || !d_gathered || !d_out || nranks < 1 || nimg < 1) return fail(SNES_E_INVALID, "snes_merge_best_dev: bad argument");
+    RET(set_device(ctx));
+    LAUNCH(ctx, "k_merge_best", k_merge_best<<<(nimg + 127) / 128, 128, 0, ctx->stream>>>(reinterpret_cast<const Best *>(d_gathered), nranks, nimg,
+                                                           reinterpret_cast<Best *>(d_out)));
+    return SNES_OK;
+}
+
 extern "C" int snes_batch_apply_best_dev(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
                                          const uint8_t *d_cand_all, int ncand_all, const snes_best *d_best) {
     RET(bind_images(ctx, images, nimg));
     const snes_config cfg = images[0]->cfg;
     RET(check_slot(cfg, palette, index));
     if (!d_cand_all || !d_best || ncand_all < 1) return fail(SNES_E_INVALID, "snes_batch_apply_best_dev: NULL argument");
-    k_apply_best<<<(nimg + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_imgs, nimg, palette * cfg.subpalette_size + index, d_cand_all,
-                                                           ncand_all, reinterpret_cast<const Best *>(d_best), cfg.nes ? 1 : 0);
-    LAUNCHED(ctx);
+    LAUNCH(ctx, "k_apply_best", k_apply_best<<<(nimg + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_imgs, nimg, palette * cfg.subpalette_size + index, d_cand_all,
+                                                           ncand_all, reinterpret_cast<const Best *>(d_best), cfg.nes ? 1 : 0));
     return batch_optimize(ctx, images, nimg);  // lib.rs:236-237, 280-281, 324-325
 }
 
@@ -892,8 +1001,7 @@ static int batch_step(snes_ctx *ctx, snes_image *const *images, int nimg, int pa
             if (cand[i] > 32) return fail(SNES_E_INVALID, "colour component > 32");
         CK(cudaMemcpyAsync(ctx->cand, cand, E * 3, cudaMemcpyHostToDevice, st));
     } else {
-        k_make_cands<<<nimg, 64, 0, st>>>(ctx->d_imgs, slot, mode == 1 ? -1 : channel, ctx->cand, ncand);
-        LAUNCHED(ctx);
+        LAUNCH(ctx, "k_make_cands", k_make_cands<<<nimg, 64, 0, st>>>(ctx->d_imgs, slot, mode == 1 ? -1 : channel, ctx->cand, ncand));
     }
     if (mode != 1) RET(batch_error(ctx, images, nimg));  // best_error = self.error() (lib.rs:199, 294)
     EvalPlan pl;
@@ -904,10 +1012,8 @@ static int batch_step(snes_ctx *ctx, snes_image *const *images, int nimg, int pa
     pl.do_assign = pl.do_score = true;
     pl.d_scores = ctx->scores;
     RET(run_plan(ctx, cfg, pl));
-    k_argmin<<<nimg, 128, 0, st>>>(ctx->scores, ncand, 0, ctx->best);
-    LAUNCHED(ctx);
-    k_apply_best<<<(nimg + 127) / 128, 128, 0, st>>>(ctx->d_imgs, nimg, slot, ctx->cand, ncand, ctx->best, mode == 1);
-    LAUNCHED(ctx);
+    LAUNCH(ctx, "k_argmin", k_argmin<<<nimg, 128, 0, st>>>(ctx->scores, ncand, 0, ctx->best));
+    LAUNCH(ctx, "k_apply_best", k_apply_best<<<(nimg + 127) / 128, 128, 0, st>>>(ctx->d_imgs, nimg, slot, ctx->cand, ncand, ctx->best, mode == 1));
     RET(batch_optimize(ctx, images, nimg));
     if (best) CK(cudaMemcpyAsync(best, ctx->best, sizeof(Best) * nimg, cudaMemcpyDeviceToHost, st));
     if (errors_after) {
@@ -1014,8 +1120,7 @@ extern "C" int snes_closest_color_index(snes_ctx *ctx, const uint8_t *colors5, i
         CK(cudaMalloc((void **)&d_o, sizeof(int32_t) * n));
         CK(cudaMemcpyAsync(d_c, colors5, (size_t)ncolors * 3, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(d_t, targets, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
-        k_closest<<<(n + 127) / 128, 128, 0, st>>>(d_c, ncolors, d_t, n, cielab, ctx->labtab, d_o);
-        LAUNCHED(ctx);
+        LAUNCH(ctx, "k_closest", k_closest<<<(n + 127) / 128, 128, 0, st>>>(d_c, ncolors, d_t, n, cielab, ctx->labtab, d_o));
         CK(cudaMemcpyAsync(out_index, d_o, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         return SNES_OK;
@@ -1038,8 +1143,7 @@ extern "C" int snes_new_nes_only(snes_ctx *ctx, const uint8_t *colors5, int n, i
         CK(cudaMalloc((void **)&d_c, (size_t)n * 3));
         CK(cudaMalloc((void **)&d_o, (size_t)n * 3));
         CK(cudaMemcpyAsync(d_c, colors5, (size_t)n * 3, cudaMemcpyHostToDevice, st));
-        k_nes_only<<<(n + 127) / 128, 128, 0, st>>>(d_c, n, cielab, ctx->labtab, d_o);
-        LAUNCHED(ctx);
+        LAUNCH(ctx, "k_nes_only", k_nes_only<<<(n + 127) / 128, 128, 0, st>>>(d_c, n, cielab, ctx->labtab, d_o));
         CK(cudaMemcpyAsync(out5, d_o, (size_t)n * 3, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         return SNES_OK;

@@ -1,0 +1,173 @@
+"""Headless optimiser driver: the schedule of `run()` (/root/reference/src/lib.rs:881-933) without the
+SDL window, for one image or a batch of independent images, on one GPU or sharded over the GPUs of
+one box (one process per GPU, `torch.distributed`).
+
+Sharding: the candidate evaluations of one optimiser step are independent, so rank r
+evaluates the candidate slice [r*n/R, (r+1)*n/R) of every image.  The only exchange is the argmin:
+each rank's per-image (error, global candidate index) pair -- 16 bytes per image -- is all-gathered
+(NCCL over NVLink on GPUs, gloo in the CPU tests of the host logic) and every rank takes the same
+lexicographic minimum, which reproduces the reference's strict-`<`, lowest-index-wins rule
+(lib.rs:216) for any R.  Every rank then applies the accept rule to its own replica of the images, so
+replicas stay bit-identical without further communication.
+
+torch is plumbing here (device buffers, streams, the process group); the arithmetic is libsnesgpu's.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import engine, synth
+
+
+# ---- schedule (lib.rs:881-933) -------------------------------------------------------------------------
+@dataclass
+class Cursor:
+    """The optimiser cursor of run(): (palette, palette_index, channel, step)."""
+    palette: int = 0
+    palette_index: int = 0
+    channel: int = 0
+    step: int = 0
+
+    def mode(self, config: engine.Config) -> str:
+        if config.nes:                      # lib.rs:892
+            return "nes"
+        return "random" if self.step % 5 < 4 else "channel"   # lib.rs:890
+
+    def advance(self, config: engine.Config):
+        """lib.rs:917-932"""
+        random = self.step % 5 < 4
+        self.channel += 1
+        if self.channel == 3 or random:
+            self.channel = 0
+            self.palette_index += 1
+            if self.palette_index == config.subpalette_size:
+                self.palette_index = 0
+                self.palette += 1
+                if self.palette == config.subpalette_count:
+                    self.palette = 0
+                    self.step += 1
+
+
+def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous candidate slice of `rank`: [rank*n/world, (rank+1)*n/world)."""
+    return (rank * n) // world, ((rank + 1) * n) // world
+
+
+def merge_best_host(gathered: np.ndarray) -> np.ndarray:
+    """Host restatement of k_merge_best for the gloo tests: gathered is (R, nimg) of BEST_DTYPE with
+    global candidate indices; returns the lexicographic minimum of (err, idx) per image."""
+    out = gathered[0].copy()
+    for r in range(1, gathered.shape[0]):
+        o = gathered[r]
+        take = (o["idx"] >= 0) & ((out["idx"] < 0) | (o["err"] < out["err"]) | ((o["err"] == out["err"]) & (o["idx"] < out["idx"])))
+        out[take] = o[take]
+    return out
+
+
+class BatchOptimizer:
+    """A batch of independent OptimizedImages advancing through the reference's schedule together,
+    with the candidates of every step sharded over the ranks of `group`."""
+
+    def __init__(self, ctx: engine.Context, images: Sequence[engine.OptimizedImage], rank: int = 0, world: int = 1,
+                 group=None, seed: int = 0):
+        import torch
+        self.torch = torch
+        self.ctx = ctx
+        self.images = list(images)
+        self.config = self.images[0].config
+        self.rank, self.world, self.group = rank, world, group
+        self.seed = seed
+        self.cursor = Cursor()
+        self.iteration = 0
+        self.device = torch.device("cuda", ctx.device)
+        nimg = len(self.images)
+        self._best_local = torch.zeros(nimg * 2, dtype=torch.int64, device=self.device)   # nimg x 16 bytes
+        self._best_all = torch.zeros(world * nimg * 2, dtype=torch.int64, device=self.device)
+        self._best = torch.zeros(nimg * 2, dtype=torch.int64, device=self.device)
+        self._errors = torch.zeros(nimg, dtype=torch.float64, device=self.device)
+        # enqueue library work on torch's current stream so it orders with the collectives and is seen by
+        # torch.cuda.Event timing; torch reports the legacy default stream as handle 0, which the C ABI reads as
+        # "own stream", so name it explicitly (cudaStreamLegacy == 0x1)
+        ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream or 1)
+
+    # ---- candidate lists ---------------------------------------------------------------------------
+    def candidates_host(self, ncand_total: int) -> np.ndarray:
+        """The explicit, seeded stand-in for the 64 rand::rng() draws of lib.rs:205-208, per image."""
+        return np.stack([synth.candidates(self.seed * 1000003 + j, self.iteration, ncand_total) for j in range(len(self.images))])
+
+    # ---- one optimize_palette_entry_random over the batch, device-resident inputs ----------------------
+    def step_random_dev(self, d_cand_all, ncand_total: int):
+        """d_cand_all: uint8 CUDA tensor (nimg, ncand_total, 3), identical on every rank."""
+        torch = self.torch
+        nimg = len(self.images)
+        p, i = self.cursor.palette, self.cursor.palette_index
+        lo, hi = shard_bounds(ncand_total, self.rank, self.world)
+        engine.batch_error_dev(self.images)                                   # best_error = self.error()  (lib.rs:199)
+        if self.world == 1:
+            engine.batch_eval_candidates_dev(self.images, p, i, d_cand_all.data_ptr(), ncand_total, 0, None, self._best.data_ptr())
+        else:
+            # this rank's slice, made contiguous per image
+            d_slice = d_cand_all[:, lo:hi, :].contiguous()
+            engine.batch_eval_candidates_dev(self.images, p, i, d_slice.data_ptr(), hi - lo, lo, None, self._best_local.data_ptr())
+            torch.distributed.all_gather_into_tensor(self._best_all, self._best_local, group=self.group)
+            engine.merge_best_dev(self.ctx, self._best_all.data_ptr(), self.world, nimg, self._best.data_ptr())
+        # accept if strictly better, then optimize() with the winner (lib.rs:216-219, 236-237)
+        engine.batch_apply_best_dev(self.images, p, i, d_cand_all.data_ptr(), ncand_total, self._best.data_ptr())
+        self.cursor.advance(self.config)
+        self.iteration += 1
+
+    # ---- the same through host buffers (the call a user of the library makes) --------------------------
+    def step_random_host(self, cand_all_pinned, d_cand_all, best_pinned):
+        """cand_all_pinned: pinned CPU uint8 tensor (nimg, ncand_total, 3); d_cand_all: its device staging
+        buffer; best_pinned: pinned CPU int64 tensor (nimg*2) receiving the winning (err, idx) records."""
+        d_cand_all.copy_(cand_all_pinned, non_blocking=True)
+        self.step_random_dev(d_cand_all, cand_all_pinned.shape[1])
+        best_pinned.copy_(self._best, non_blocking=True)
+        self.torch.cuda.current_stream(self.device).synchronize()
+        return best_pinned
+
+    def best_records(self) -> np.ndarray:
+        return self._best.cpu().numpy().view(engine.BEST_DTYPE)
+
+
+class HeadlessRunner:
+    """`run()` of the reference without the window: initialize_tiles -> recalculate_palettes -> N
+    iterations of the optimiser schedule -> JSON (lib.rs:851-853, 987-989, 889-933, 999-1003)."""
+
+    def __init__(self, ctx: engine.Context, rgba: np.ndarray, config: engine.Config, seed: int = 0, ncand: int = 64):
+        self.image = engine.OptimizedImage(ctx, rgba, config)
+        self.config = config
+        self.cursor = Cursor()
+        self.seed, self.ncand = seed, ncand
+        self.iteration = 0
+        self.last_error = float("inf")
+        self.log: List[float] = []
+
+    def initialize(self):
+        self.image.initialize_tiles()        # lib.rs:851
+        self.image.recalculate_palettes()    # green button, lib.rs:987-989
+
+    def iterate(self, n: int = 1):
+        im, c = self.image, self.cursor
+        for _ in range(n):
+            mode = c.mode(self.config)
+            if mode == "nes":
+                im.optimize_palette_entry_nes(c.palette, c.palette_index)
+            elif mode == "random":
+                im.optimize_palette_entry_random(c.palette, c.palette_index, synth.candidates(self.seed, self.iteration, self.ncand))
+            else:
+                im.optimize_palette_entry_channel(c.palette, c.palette_index, c.channel)
+            im.optimize()                    # lib.rs:906-908
+            error = im.error()               # lib.rs:910
+            if abs(error - self.last_error) > np.finfo(np.float64).eps:
+                self.last_error = error
+                self.log.append(error)
+            c.advance(self.config)
+            self.iteration += 1
+
+    def write_json(self, path: str):
+        with open(path, "w") as f:           # lib.rs:999-1003
+            f.write(self.image.as_json_string())

@@ -81,6 +81,9 @@ _SIGNATURES = {
     "snes_ctx_set_stream": (_i, [_vp, _vp]),
     "snes_ctx_synchronize": (_i, [_vp]),
     "snes_ctx_set_chunk": (_i, [_vp, _i]),
+    "snes_ctx_set_scorer": (_i, [_vp, _i, _i]),
+    "snes_ctx_profile_begin": (_i, [_vp]),
+    "snes_ctx_profile_end": (_i, [_vp, _vp, _sz, C.POINTER(_sz)]),
     "snes_image_new": (_i, [_vp, _vp, _i, _i, C.POINTER(_Config), C.POINTER(_vp)]),
     "snes_image_free": (None, [_vp]),
     "snes_image_initialize_tiles": (_i, [_vp]),
@@ -106,6 +109,7 @@ _SIGNATURES = {
     "snes_batch_eval_candidates": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "snes_batch_eval_candidates_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "snes_batch_apply_best_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "snes_merge_best_dev": (_i, [_vp, _vp, _i, _i, _vp]),
     "snes_batch_step_random": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),
     "snes_batch_step_nes": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "snes_batch_step_channel": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
@@ -187,6 +191,19 @@ class Context:
 
     def set_chunk(self, evaluations: int):
         _check(self._l.snes_ctx_set_chunk(self._h, int(evaluations)), "snes_ctx_set_chunk")
+
+    def set_scorer(self, fused: bool = True, block_width: int = 32):
+        _check(self._l.snes_ctx_set_scorer(self._h, int(fused), int(block_width)), "snes_ctx_set_scorer")
+
+    def profile_begin(self):
+        _check(self._l.snes_ctx_profile_begin(self._h), "snes_ctx_profile_begin")
+
+    def profile_end(self) -> dict:
+        """Per-kernel device time since profile_begin(): {kernel: {"ms": total, "n": launches}}."""
+        buf = C.create_string_buffer(1 << 16)
+        n = _sz(0)
+        _check(self._l.snes_ctx_profile_end(self._h, buf, len(buf), C.byref(n)), "snes_ctx_profile_end")
+        return json.loads(buf.value.decode("ascii"))
 
     def synchronize(self):
         _check(self._l.snes_ctx_synchronize(self._h), "snes_ctx_synchronize")
@@ -436,3 +453,7 @@ def batch_apply_best_dev(images: Sequence[OptimizedImage], palette: int, index: 
     ctx = _ctx_of(images)
     _check(ctx._l.snes_batch_apply_best_dev(ctx._h, _handles(images), len(images), palette, index, d_cand_all, ncand_all, d_best),
            "snes_batch_apply_best_dev")
+
+
+def merge_best_dev(ctx: Context, d_gathered: int, nranks: int, nimg: int, d_out: int):
+    _check(ctx._l.snes_merge_best_dev(ctx._h, d_gathered, nranks, nimg, d_out), "snes_merge_best_dev")

