@@ -74,10 +74,12 @@ int snes_ctx_synchronize(snes_ctx *ctx);
  * (at most cap-1 bytes + NUL; *len = full length). */
 int snes_ctx_profile_begin(snes_ctx *ctx);
 int snes_ctx_profile_end(snes_ctx *ctx, char *buf, size_t cap, size_t *len);
-/* scorer selection: fused != 0 -> k_score_fused (blur planes stay in shared memory; default), 0 -> the
- * multi-kernel pipeline that spills them to HBM (kept for A/B checks); block_width 16 or 32.
- * Env overrides at context creation: SNESGPU_FUSED, SNESGPU_BW. */
-int snes_ctx_set_scorer(snes_ctx *ctx, int fused, int block_width);
+/* kernel selection (all variants give the same results; kept switchable for A/B checks):
+ *   fused != 0        k_score_fused, blur planes stay in shared memory (default); 0 = multi-kernel pipeline via HBM
+ *   block_width       column block of the fused scorer, 16 or 32
+ *   delta_assign != 0 without dithering, a candidate re-decides only the pixels its entry can change (default)
+ * Env overrides at context creation: SNESGPU_FUSED, SNESGPU_BW, SNESGPU_DELTA. */
+int snes_ctx_set_scorer(snes_ctx *ctx, int fused, int block_width, int delta_assign);
 /* how many candidate evaluations have their scratch live at once (default 256, env SNESGPU_CHUNK) */
 int snes_ctx_set_chunk(snes_ctx *ctx, int evaluations);
 

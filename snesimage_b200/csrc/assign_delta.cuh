@@ -1,0 +1,273 @@
+// Candidate evaluation without dithering: optimize() (lib.rs:425-501) restricted to what a candidate can change.
+//
+// A candidate replaces ONE entry (slot `ovr` = palette*S + index) of the image's palette
+// (lib.rs:205-220, 252-262, 296-306).  Without error diffusion every pixel is decided on its own
+// (lib.rs:447-451), so only pixels of tiles bound to that subpalette can change, and for those the
+// reference's strict-< first-minimum over the S entries equals
+//        combine( first-minimum over the entries j != index  ,  the candidate's own distance )
+// with ties going to the lower index.  The first part does not depend on the candidate:
+//
+//   k_assign_prepare   once per image per step: base assignment of every pixel under the current palette as a
+//                      global entry index (gi), and for pixels of the affected tiles the excluded-entry
+//                      minimum (key, index).
+//   k_assign_pyr       once per candidate: one distance per affected pixel -> gi map of the candidate, fused
+//                      with the coarse scales (>= 1) of its XYB pyramid, which need every pixel anyway.
+//
+// Results are identical to running the full S-entry search per candidate (tests compare both paths with
+// the oracle).  RGB keys are the int32 red-mean key; Lab keys are the f32 CIEDE2000 distances (bit pattern
+// stored as int).
+#pragma once
+#include "kernels.cuh"
+#include "lab.cuh"
+
+namespace snes {
+
+// grid = (64, nimg), block 256, 4 horizontally adjacent pixels per thread
+template <bool LAB>
+__global__ void __launch_bounds__(256) k_assign_prepare(const ImgDev *imgs, int S, int CS, int ovr) {
+    __shared__ uchar4 pal[MAX_ENTRIES];
+    __shared__ float4 pal_lab[LAB ? MAX_ENTRIES : 1];
+    const ImgDev im = imgs[blockIdx.y];
+    const int tid = threadIdx.x;
+    for (int j = tid; j < CS; j += 256) {
+        pal[j] = im.tables->rgb8[j];
+        if (LAB) pal_lab[j] = make_float4(im.tables->lab[j][0], im.tables->lab[j][1], im.tables->lab[j][2], 0.0f);
+    }
+    __syncthreads();
+    const int q = blockIdx.x * 256 + tid, px0 = q * 4, y = px0 >> 8, x = px0 & 255;
+    const int sub = im.tile_pal[(y >> 3) * 32 + (x >> 3)] * S;
+    const int psub = (ovr / S) * S, oloc = ovr - psub;
+    const bool affected = sub == psub;
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(im.rgba) + q);
+    const uint32_t pix[4] = {v.x, v.y, v.z, v.w};
+    uint32_t gi4 = 0, ei4 = 0;
+    int ek[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int r = pix[k] & 255, g = (pix[k] >> 8) & 255, b = (pix[k] >> 16) & 255, a = pix[k] >> 24;
+        int bi = 0, xi = 0;
+        int xkey;
+        if (LAB) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(im.lab) + px0 + k);
+            float best = __int_as_float(0x7f800000), xbest = __int_as_float(0x7f800000);
+            for (int j = 0; j < S; j++) {
+                const float4 c = pal_lab[sub + j];
+                const float d = ciede2000(c.x, c.y, c.z, t.x, t.y, t.z);
+                if (d < best) {
+                    best = d;
+                    bi = j;
+                }
+                if (j != oloc && d < xbest) {
+                    xbest = d;
+                    xi = j;
+                }
+            }
+            xkey = __float_as_int(xbest);
+        } else {
+            int best = 0x7fffffff, xbest = 0x7fffffff;
+            for (int j = 0; j < S; j++) {
+                const uchar4 c = pal[sub + j];
+                const int key = redmean_key(c.x, c.y, c.z, r, g, b);
+                if (key < best) {
+                    best = key;
+                    bi = j;
+                }
+                if (j != oloc && key < xbest) {
+                    xbest = key;
+                    xi = j;
+                }
+            }
+            xkey = xbest;
+        }
+        gi4 |= (uint32_t)(a > 0 ? sub + bi : GI_BLACK) << (8 * k);
+        ei4 |= (uint32_t)((affected && a > 0) ? xi : 0xFF) << (8 * k);   // 0xFF: this pixel cannot change
+        ek[k] = xkey;
+    }
+    reinterpret_cast<uint32_t *>(im.base_gi)[q] = gi4;
+    reinterpret_cast<uint32_t *>(im.excl_idx)[q] = ei4;
+    if (affected) reinterpret_cast<int4 *>(im.excl_key)[q] = make_int4(ek[0], ek[1], ek[2], ek[3]);
+}
+
+// k_assign_pyr: grid = (4, evaluations of the chunk), block 256; a CTA owns one 128x128 quadrant.
+//   MODE 0 / 1: delta assignment with the red-mean key / CIEDE2000 (writes the candidate's gi map)
+//   MODE 2    : the gi map already exists (written by k_assign_dither); only the pyramid is built
+// and in every mode the row-major XYB planes of scales 1..5 (the fused scorer's inputs): a thread takes
+// 4x4 scale-0 pixels -> 2x2 pixels of scale 1 and one of scale 2; scales 3..5 go through shared memory
+// (downscale_by_2 on linear RGB, then linear_rgb_to_xyb + make_positive_xyb, as ssimulacra2 does).
+template <int MODE>
+__global__ void __launch_bounds__(256) k_assign_pyr(const ImgDev *imgs, const CandEntry *cents, int ncand, int e0, int S, int CS,
+                                                    int ovr, uint8_t *maps, float *xyb_rm_base) {
+    __shared__ float s_lin[MAX_ENTRIES + 1][3];
+    __shared__ float s2[3][32][33];   // linear RGB of the quadrant at scale 2
+    __shared__ float s3[3][16][17];
+    __shared__ float s4[3][8][9];
+    const int e = blockIdx.y, ea = e0 + e, img = ea / ncand, tid = threadIdx.x;
+    const int qx0 = (blockIdx.x & 1) * 128, qy0 = (blockIdx.x >> 1) * 128;
+    const ImgDev im = imgs[img];
+    float *rm = xyb_rm_base + (size_t)e * EVAL_XYB_FLOATS;
+    uint8_t *map = maps + (size_t)e * NPIX;
+    const CandEntry ce = cents[ea];
+    for (int j = tid; j < CS; j += 256)
+        for (int c = 0; c < 3; c++) s_lin[j][c] = (j == ovr) ? ce.lin[c] : im.tables->lin[j][c];
+    if (tid < 3) {
+        s_lin[BLACK][tid] = im.tables->lin[BLACK][tid];
+        s_lin[GI_BLACK][tid] = im.tables->lin[BLACK][tid];   // C*S <= 255 on this path: slot 255 is free
+    }
+    const int psub = (ovr / S) * S, oloc = ovr - psub;
+    const int cr = ce.rgb8.x, cg = ce.rgb8.y, cb = ce.rgb8.z;
+    __syncthreads();
+
+    auto store_xyb = [&](int L, int x, int y, const float lin[3]) {
+        const int d = W >> L;
+        float xv, yv, bv;
+        lin_to_pxyb(lin[0], lin[1], lin[2], xv, yv, bv);
+        const size_t o = 3 * (size_t)scale_off(L) + (size_t)y * d + x;
+        rm[o] = xv;
+        rm[o + (size_t)d * d] = yv;
+        rm[o + 2 * (size_t)d * d] = bv;
+    };
+
+    // ---- scales 0 (gi map), 1 and 2: 32x32 blocks of 4x4 pixels, 4 blocks per thread -----------------------------------------
+#pragma unroll 1
+    for (int it = 0; it < 4; it++) {
+        const int bx = tid & 31, by = it * 8 + (tid >> 5);   // block inside the quadrant
+        const int x0 = qx0 + 4 * bx, y0 = qy0 + 4 * by;
+        uint32_t g4[4], e4[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int px = (y0 + r) * W + x0;
+            if (MODE == 2) {
+                g4[r] = __ldg(reinterpret_cast<const uint32_t *>(map + px));
+                e4[r] = 0xffffffffu;
+            } else {
+                g4[r] = __ldg(reinterpret_cast<const uint32_t *>(im.base_gi + px));
+                e4[r] = __ldg(reinterpret_cast<const uint32_t *>(im.excl_idx + px));
+            }
+        }
+        // MODE 1: CIEDE2000 is expensive and only ~1/C of the blocks are affected, so the warp pools them: two affected
+        // blocks at a time, one pixel per lane, and the 16 decisions of a block return to its owner through a ballot
+        uint32_t takebits = 0;
+        if (MODE == 1) {
+            const int lane = tid & 31;
+            const bool aff = (e4[0] & e4[1] & e4[2] & e4[3]) != 0xffffffffu;
+            unsigned mask = __ballot_sync(0xffffffffu, aff);
+            while (mask) {
+                const int sa = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const bool hasb = mask != 0;
+                const int sb = hasb ? __ffs(mask) - 1 : sa;
+                if (hasb) mask &= mask - 1;
+                const int src = lane < 16 ? sa : sb;
+                const int pix = lane & 15, r = pix >> 2, c = pix & 3;
+                const int sx0 = __shfl_sync(0xffffffffu, x0, src), sy0 = __shfl_sync(0xffffffffu, y0, src);
+                const uint32_t w0 = __shfl_sync(0xffffffffu, e4[0], src), w1 = __shfl_sync(0xffffffffu, e4[1], src);
+                const uint32_t w2 = __shfl_sync(0xffffffffu, e4[2], src), w3 = __shfl_sync(0xffffffffu, e4[3], src);
+                const uint32_t w = r == 0 ? w0 : (r == 1 ? w1 : (r == 2 ? w2 : w3));
+                const int xi = (w >> (8 * c)) & 255;
+                bool take = false;
+                if (xi != 0xFF && (lane < 16 || hasb)) {
+                    const int px = (sy0 + r) * W + sx0 + c;
+                    const float4 t = __ldg(reinterpret_cast<const float4 *>(im.lab) + px);
+                    const float d = ciede2000(ce.lab[0], ce.lab[1], ce.lab[2], t.x, t.y, t.z);
+                    const float xb = __int_as_float(__ldg(im.excl_key + px));
+                    take = d < xb || (d == xb && oloc < xi);
+                }
+                const unsigned tb = __ballot_sync(0xffffffffu, take);
+                if (lane == sa) takebits = tb & 0xffffu;
+                if (hasb && lane == sb) takebits = tb >> 16;
+            }
+        }
+        float l1[2][2][3];
+        float quad[4][4][3];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            uint32_t out4 = g4[r];
+            if (MODE != 2 && e4[r] != 0xffffffffu) {
+                out4 = 0;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    int gi = (g4[r] >> (8 * c)) & 255;
+                    const int xi = (e4[r] >> (8 * c)) & 255;
+                    if (xi != 0xFF) {   // affected tile, opaque pixel: candidate entry vs the best of the others
+                        bool take;
+                        if (MODE == 1) {
+                            take = (takebits >> (4 * r + c)) & 1;
+                        } else {
+                            const int px = (y0 + r) * W + x0 + c;
+                            const int xkey = __ldg(im.excl_key + px);
+                            const uchar4 p = __ldg(im.rgba + px);
+                            const int key = redmean_key(cr, cg, cb, p.x, p.y, p.z);
+                            take = key < xkey || (key == xkey && oloc < xi);
+                        }
+                        gi = psub + (take ? oloc : xi);
+                    }
+                    out4 |= (uint32_t)gi << (8 * c);
+                }
+            }
+            if (MODE != 2) *reinterpret_cast<uint32_t *>(map + (y0 + r) * W + x0) = out4;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int gi = (out4 >> (8 * c)) & 255;
+                quad[r][c][0] = s_lin[gi][0];
+                quad[r][c][1] = s_lin[gi][1];
+                quad[r][c][2] = s_lin[gi][2];
+            }
+        }
+        // downscale_by_2: ((p00 + p01) + p10) + p11, * 0.25  (row-major 2x2 order of the crate's loop)
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int b = 0; b < 2; b++)
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                    l1[a][b][c] = (((quad[2 * a][2 * b][c] + quad[2 * a][2 * b + 1][c]) + quad[2 * a + 1][2 * b][c]) +
+                                   quad[2 * a + 1][2 * b + 1][c]) * 0.25f;
+        float l2[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) l2[c] = (((l1[0][0][c] + l1[0][1][c]) + l1[1][0][c]) + l1[1][1][c]) * 0.25f;
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int b = 0; b < 2; b++) store_xyb(1, (x0 >> 1) + b, (y0 >> 1) + a, l1[a][b]);
+        store_xyb(2, x0 >> 2, y0 >> 2, l2);
+        s2[0][by][bx] = l2[0];
+        s2[1][by][bx] = l2[1];
+        s2[2][by][bx] = l2[2];
+    }
+    __syncthreads();
+    // ---- scale 3: 16x16 per quadrant, one pixel per thread ------------------------------------------------------------------
+    {
+        const int ax = tid & 15, ay = tid >> 4;
+        float l3[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+            l3[c] = (((s2[c][2 * ay][2 * ax] + s2[c][2 * ay][2 * ax + 1]) + s2[c][2 * ay + 1][2 * ax]) + s2[c][2 * ay + 1][2 * ax + 1]) * 0.25f;
+        store_xyb(3, (qx0 >> 3) + ax, (qy0 >> 3) + ay, l3);
+        s3[0][ay][ax] = l3[0];
+        s3[1][ay][ax] = l3[1];
+        s3[2][ay][ax] = l3[2];
+    }
+    __syncthreads();
+    if (tid < 64) {   // scale 4: 8x8
+        const int ax = tid & 7, ay = tid >> 3;
+        float l4[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+            l4[c] = (((s3[c][2 * ay][2 * ax] + s3[c][2 * ay][2 * ax + 1]) + s3[c][2 * ay + 1][2 * ax]) + s3[c][2 * ay + 1][2 * ax + 1]) * 0.25f;
+        store_xyb(4, (qx0 >> 4) + ax, (qy0 >> 4) + ay, l4);
+        s4[0][ay][ax] = l4[0];
+        s4[1][ay][ax] = l4[1];
+        s4[2][ay][ax] = l4[2];
+    }
+    __syncthreads();
+    if (tid < 16) {   // scale 5: 4x4
+        const int ax = tid & 3, ay = tid >> 2;
+        float l5[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+            l5[c] = (((s4[c][2 * ay][2 * ax] + s4[c][2 * ay][2 * ax + 1]) + s4[c][2 * ay + 1][2 * ax]) + s4[c][2 * ay + 1][2 * ax + 1]) * 0.25f;
+        store_xyb(5, (qx0 >> 5) + ax, (qy0 >> 5) + ay, l5);
+    }
+}
+
+}  // namespace snes

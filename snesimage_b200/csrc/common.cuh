@@ -60,6 +60,10 @@ struct ImgDev {
     double *cur_err;          // error() of the current state
     const float *lab;         // per-pixel Lab of the original (perceptual mode), [NPIX][4]
     const uint8_t *alpha;     // alpha channel of the original, [NPIX]
+    // per-step scratch of the no-dither candidate path (assign_delta.cuh)
+    uint8_t *base_gi;         // [NPIX] assignment under the current palette as global entry index (GI_BLACK: transparent)
+    uint8_t *excl_idx;        // [NPIX] best entry other than the replaced one, 0xFF where the pixel cannot change
+    int *excl_key;            // [NPIX] its key (int32 red-mean key, or f32 CIEDE2000 bits)
 };
 
 struct Best {

@@ -38,11 +38,13 @@ struct FusedSmem {
     static constexpr int NCOL = BW + 10;  // 6 halo columns on the left, 4 on the right
     static constexpr int IP = BW + 11;    // odd pitch: lane = row reads are conflict-free
     static constexpr int HP = BW + 1;
+    static constexpr int NW = (BW + 16) / 4;
     float hout[3][HB + 10][HP];
     float in2[HB + 4][IP];   // i2 of rows r0-4 .. r0+HB-1 (the 4 extra rows serve the lagging maps)
     float in1[HB + 4][IP];   // i1 of the same tile
     float xyb[MAX_ENTRIES + 1];
     double red[FUSED_WARPS][NSUMS];
+    uint32_t raw[HB + 4][NW];   // scale 0: palette_map bytes of the tile, aligned 4-pixel words (columns c0-8 .. c0+BW+7)
     uint8_t tp[NTILES];
 };
 
@@ -57,14 +59,24 @@ struct FusedArgs {
     double *partials;        // [E][NSCALES][3][NSUMS]
 };
 
-__device__ __forceinline__ void cp_async4(float *smem_dst, const float *gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+// 4-byte global -> shared copy that bypasses registers (LDGSTS); sdst is a 32-bit shared-window address
+__device__ __forceinline__ void cp_async4(unsigned sdst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sdst), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-// max(x, 0.0) with fmax's NaN behaviour (NaN -> 0), without fmax's full IEEE sequence
-__device__ __forceinline__ double relu64(double x) { return x > 0.0 ? x : 0.0; }
+// x / y for 1 <= y < 2^100 in f64 without the slow-path checks of the generic division: f32 reciprocal seed,
+// two Newton steps, one residual correction (Markstein).  Correctly rounded except for rare last-bit cases.
+__device__ __forceinline__ double div64_fast(double x, double y) {
+    double r = (double)__frcp_rn((float)y);
+    double e = fma(-y, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-y, r, 1.0);
+    r = fma(r, e, r);
+    const double q = x * r;
+    return fma(fma(-y, q, x), r, q);
+}
 
 template <int D, int BW0, typename SM>
 __device__ __forceinline__ void fused_scale(SM &sm, const FusedArgs &a, const ImgDev &im, const uint8_t *map, int e, int ea,
@@ -103,43 +115,65 @@ __device__ __forceinline__ void fused_scale(SM &sm, const FusedArgs &a, const Im
             const int y_lo = r0 - 4 < 0 ? 0 : r0 - 4;        // first staged image row; buffer row = y - (r0 - 4)
             const int nrows = r0 + HB - y_lo;
             // ---- stage the tile (rows y_lo .. r0+HB-1, columns c0-6 .. c0+BW+3; zero outside the image) ----------
-            // one row per warp iteration, lane = column.  f32 planes go global -> smem with 4-byte cp.async (all of a
-            // thread's loads in flight at once); at scale 0 the rendered pixel is a table lookup of its palette
-            // entry (as_rgba, lib.rs:550-577), with the byte loads of UR rows issued ahead of their use.
+            // Everything goes global -> smem with 4-byte cp.async, so all of a thread's loads are in flight at once and
+            // cost no registers: i1 (and i2 at scales >= 1) one row per warp iteration, lane = column; at scale 0 the
+            // palette_map bytes as aligned words (two rows per warp iteration), converted after the wait by the thread
+            // that fetched them -- the rendered pixel is a table lookup of its palette entry (as_rgba, lib.rs:550-577).
             {
-                constexpr int UR = 4;
-#pragma unroll 1
-                for (int rb = warp; rb < nrows; rb += UR * FUSED_WARPS) {
+                const unsigned s_in1 = smem_addr(&sm.in1[0][0]), s_in2 = smem_addr(&sm.in2[0][0]);
+                const int ry_lo = y_lo - (r0 - 4);
 #pragma unroll
-                    for (int kk = 0; kk < NCOL; kk += 32) {
-                        const int k = kk + lane, x = c0 - 6 + k;
-                        const bool kin = k < NCOL;
-                        const bool xin = kin && x >= 0 && x < D;
-                        int gi[UR];
-#pragma unroll
-                        for (int u = 0; u < UR; u++) {
-                            const int r = rb + u * FUSED_WARPS, y = y_lo + r;
-                            gi[u] = 0;
-                            if (D == W && xin && r < nrows) {
-                                const int px = y * W + x;
-                                if (a.gi_fmt) {
-                                    gi[u] = __ldg(map + px);
-                                } else {
-                                    gi[u] = __ldg(im.alpha + px) ? sm.tp[(y >> 3) * 32 + (x >> 3)] + __ldg(map + px) : BLACK;
-                                }
+                for (int kk = 0; kk < NCOL; kk += 32) {
+                    const int k = kk + lane, x = c0 - 6 + k;
+                    if (k < NCOL) {
+                        const bool xin = x >= 0 && x < D;
+                        const float *g1 = i1p + (size_t)(y_lo + warp) * D + x;
+                        const float *g2 = i2p + (size_t)(y_lo + warp) * D + x;
+                        unsigned so = ((ry_lo + warp) * SM::IP + k) * 4;
+                        for (int r = warp; r < nrows; r += FUSED_WARPS) {
+                            if (xin) {
+                                cp_async4(s_in1 + so, g1);
+                                if (D != W) cp_async4(s_in2 + so, g2);
+                            } else {
+                                sm.in1[ry_lo + r][k] = 0.0f;
+                                sm.in2[ry_lo + r][k] = 0.0f;
                             }
+                            g1 += FUSED_WARPS * D;
+                            g2 += FUSED_WARPS * D;
+                            so += FUSED_WARPS * SM::IP * 4;
                         }
+                    }
+                }
+                if (D == W) {
+                    const int w4 = lane & 15, rs = lane >> 4;      // word within the row, row parity
+                    const int x0 = c0 - 8 + 4 * w4;
+                    const bool win = w4 < SM::NW && x0 >= 0 && x0 < D;
+                    if (win) {
+                        const uint8_t *gm = map + (y_lo + 2 * warp + rs) * W + x0;
+                        unsigned so = smem_addr(&sm.raw[ry_lo + 2 * warp + rs][w4]);
+                        for (int r = 2 * warp + rs; r < nrows; r += 2 * FUSED_WARPS) {
+                            cp_async4(so, gm);
+                            gm += 2 * FUSED_WARPS * W;
+                            so += 2 * FUSED_WARPS * SM::NW * 4;
+                        }
+                    }
+                    cp_async_wait_all();
+                    if (win) {
+                        for (int r = 2 * warp + rs; r < nrows; r += 2 * FUSED_WARPS) {
+                            const int y = y_lo + r, ry = ry_lo + r;
+                            const uint32_t mw = sm.raw[ry][w4];
+                            uint32_t aw = 0xffffffffu;
+                            int sub = 0;
+                            if (!a.gi_fmt) {   // palette_map format (error() of the image's own state): needs tile and alpha
+                                aw = __ldg(reinterpret_cast<const uint32_t *>(im.alpha + y * W + x0));
+                                sub = sm.tp[(y >> 3) * 32 + (x0 >> 3)];
+                            }
 #pragma unroll
-                        for (int u = 0; u < UR; u++) {
-                            const int r = rb + u * FUSED_WARPS, y = y_lo + r, ry = y - (r0 - 4);
-                            if (kin && r < nrows) {
-                                if (xin) {
-                                    cp_async4(&sm.in1[ry][k], i1p + y * D + x);
-                                    if (D == W) sm.in2[ry][k] = sm.xyb[gi[u]];
-                                    else cp_async4(&sm.in2[ry][k], i2p + y * D + x);
-                                } else {
-                                    sm.in1[ry][k] = 0.0f;
-                                    sm.in2[ry][k] = 0.0f;
+                            for (int i = 0; i < 4; i++) {
+                                const int k = 4 * w4 - 2 + i;
+                                if (k >= 0 && k < NCOL) {
+                                    const int gi = ((aw >> (8 * i)) & 255) ? sub + ((mw >> (8 * i)) & 255) : BLACK;
+                                    sm.in2[ry][k] = sm.xyb[gi];
                                 }
                             }
                         }
@@ -251,19 +285,27 @@ __device__ __forceinline__ void fused_scale(SM &sm, const FusedArgs &a, const Im
                             const float num_m = __fmaf_rn(mu_diff, -mu_diff, 1.0f);
                             const float num_s = __fmaf_rn(2.0f, s12 - mu12, 0.0009f);
                             const float denom_s = (s11 - mu11) + (s22 - mu22) + 0.0009f;
-                            const double dv = relu64(1.0 - (double)((num_m * num_s) / denom_s));
-                            acc[0] += dv;
-                            const double dv2 = dv * dv;
-                            acc[1] += dv2 * dv2;
-                            const double d1v = (1.0 + (double)fabsf(i2 - mu2)) / (1.0 + (double)fabsf(i1 - mu1)) - 1.0;
-                            const double art = relu64(d1v);
-                            acc[2] += art;
-                            const double art2 = art * art;
-                            acc[3] += art2 * art2;
-                            const double det = relu64(-d1v);
-                            acc[4] += det;
-                            const double det2 = det * det;
-                            acc[5] += det2 * det2;
+                            // d = max(1 - q, 0): positive iff q < 1 (1 - q is exact in sign; NaN contributes 0 like fmax)
+                            const float qf = (num_m * num_s) / denom_s;
+                            if (qf < 1.0f) {
+                                const double dv = 1.0 - (double)qf;
+                                acc[0] += dv;
+                                const double dv2 = dv * dv;
+                                acc[1] += dv2 * dv2;
+                            }
+                            // d1 = (1 + |i2 - mu2|) / (1 + |i1 - mu1|) - 1; artifact = max(d1, 0), detail_lost = max(-d1, 0):
+                            // exactly one of them is |d1|, selected by the sign bit
+                            const double d1v = div64_fast(1.0 + (double)fabsf(i2 - mu2), 1.0 + (double)fabsf(i1 - mu1)) - 1.0;
+                            const double ad = fabs(d1v);
+                            const double ad2 = ad * ad;
+                            const double ad4 = ad2 * ad2;
+                            if (__double2hiint(d1v) >= 0) {
+                                acc[2] += ad;
+                                acc[3] += ad4;
+                            } else {
+                                acc[4] += ad;
+                                acc[5] += ad4;
+                            }
                         }
                     }
                 }

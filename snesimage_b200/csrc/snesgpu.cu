@@ -18,6 +18,7 @@
 #include "kmeans.cuh"
 #include "lab.cuh"
 #include "score_fused.cuh"
+#include "assign_delta.cuh"
 
 using namespace snes;
 
@@ -56,6 +57,7 @@ struct snes_ctx {
     int chunk = 256;  // evaluations whose scratch (palette_map, coarse XYB pyramid) is live at once
     int fused = 1;    // 1: k_score_fused (on-chip blur planes); 0: multi-kernel pipeline (SNESGPU_FUSED=0)
     int bw = 32;      // column-block width of the fused scorer (16 or 32, SNESGPU_BW)
+    int delta = 1;    // 1: no-dither candidates re-decide only the pixels the replaced entry can change (SNESGPU_DELTA)
 
     // per-chunk scratch
     size_t chunk_cap = 0;
@@ -225,6 +227,7 @@ extern "C" int snes_ctx_create(int device, snes_ctx **out) {
 
     if (const char *c = getenv("SNESGPU_FUSED")) ctx->fused = atoi(c) != 0;
     if (const char *c = getenv("SNESGPU_BW")) ctx->bw = atoi(c) == 16 ? 16 : 32;
+    if (const char *c = getenv("SNESGPU_DELTA")) ctx->delta = atoi(c) != 0;
 
     float lut[256], lut2[256], n2[3], d1[3];
     for (int v = 0; v < 256; v++) {
@@ -349,10 +352,11 @@ extern "C" int snes_ctx_profile_end(snes_ctx *ctx, char *buf, size_t cap, size_t
     return SNES_OK;
 }
 
-extern "C" int snes_ctx_set_scorer(snes_ctx *ctx, int fused, int block_width) {
+extern "C" int snes_ctx_set_scorer(snes_ctx *ctx, int fused, int block_width, int delta_assign) {
     if (!ctx || (block_width != 16 && block_width != 32)) return fail(SNES_E_INVALID, "snes_ctx_set_scorer: bad argument");
     ctx->fused = fused != 0;
     ctx->bw = block_width;
+    ctx->delta = delta_assign != 0;
     return SNES_OK;
 }
 
@@ -468,9 +472,43 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
     LAUNCH(ctx, "k_tables", k_tables<<<pl.nimg + (pl.ovr >= 0 ? (E + 255) / 256 : 0), 256, 0, st>>>(ctx->d_imgs, pl.nimg, CS, pl.d_cand,
                                                                           pl.ovr >= 0 ? E : 0, ctx->cents, labtab));
 
+    // no dithering + fused scorer: per-candidate work shrinks to one distance per affected pixel (assign_delta.cuh)
+    const bool delta = ctx->fused && ctx->delta && !cfg.dither && pl.do_assign && pl.do_score && !pl.self && !pl.d_maps_out &&
+                       pl.ovr >= 0 && CS <= 255;
+    if (delta) {
+        if (cfg.perceptual_palettes)
+            LAUNCH(ctx, "k_assign_prepare<true>", k_assign_prepare<true><<<dim3(64, pl.nimg), 256, 0, st>>>(ctx->d_imgs, S, CS, pl.ovr));
+        else
+            LAUNCH(ctx, "k_assign_prepare<false>", k_assign_prepare<false><<<dim3(64, pl.nimg), 256, 0, st>>>(ctx->d_imgs, S, CS, pl.ovr));
+    }
+
     for (int e0 = 0; e0 < E; e0 += chunk) {
         const int ec = E - e0 < chunk ? E - e0 : chunk;
         uint8_t *maps = pl.d_maps_out ? pl.d_maps_out + (size_t)e0 * NPIX : ctx->maps;
+        if (delta) {
+            if (cfg.perceptual_palettes)
+                LAUNCH(ctx, "k_assign_pyr<1>", k_assign_pyr<1><<<dim3(4, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, ctx->xyb_rm));
+            else
+                LAUNCH(ctx, "k_assign_pyr<0>", k_assign_pyr<0><<<dim3(4, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, ctx->xyb_rm));
+            FusedArgs fa;
+            fa.imgs = ctx->d_imgs;
+            fa.cents = ctx->cents;
+            fa.ncand = pl.ncand;
+            fa.e0 = e0;
+            fa.S = S;
+            fa.CS = CS;
+            fa.ovr = pl.ovr;
+            fa.maps = maps;
+            fa.from_image = 0;
+            fa.gi_fmt = 1;
+            fa.xyb_rm = ctx->xyb_rm;
+            fa.partials = ctx->partials;
+            if (ctx->bw == 16)
+                LAUNCH(ctx, "k_score_fused<16>", k_score_fused<16><<<dim3(3, ec), FUSED_THREADS, sizeof(FusedSmem<16>), st>>>(fa));
+            else
+                LAUNCH(ctx, "k_score_fused<32>", k_score_fused<32><<<dim3(3, ec), FUSED_THREADS, sizeof(FusedSmem<32>), st>>>(fa));
+            continue;
+        }
         // scratch maps feed only the fused scorer: write global entry indices (no tile_palettes / alpha lookups later)
         const int gi = (ctx->fused && pl.do_score && !pl.self && !pl.d_maps_out && CS <= 255) ? 1 : 0;
         if (pl.do_assign) {
@@ -486,7 +524,10 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
         }
         if (!pl.do_score) continue;
         if (ctx->fused) {
-            LAUNCH(ctx, "k_pyramid<false>", k_pyramid<false><<<dim3(16, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self,
+            if (gi)
+                LAUNCH(ctx, "k_assign_pyr<2>", k_assign_pyr<2><<<dim3(4, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, ctx->xyb_rm));
+            else
+                LAUNCH(ctx, "k_pyramid<false>", k_pyramid<false><<<dim3(16, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self,
                                                        ctx->xyb_rm, ctx->xyb_cm, 1, gi));
             FusedArgs fa;
             fa.imgs = ctx->d_imgs;
@@ -584,6 +625,7 @@ extern "C" int snes_image_new(snes_ctx *ctx, const uint8_t *rgba, int width, int
     const size_t o_tab = take(sizeof(PalTables)), o_err = take(sizeof(double));
     const size_t o_lab = take(im->cfg.perceptual_palettes ? sizeof(float4) * NPIX : 0);
     const size_t o_alpha = take(NPIX);
+    const size_t o_bgi = take(NPIX), o_xi = take(NPIX), o_xk = take(sizeof(int) * NPIX);
     cudaError_t e = cudaMalloc(&im->slab, off);
     if (e != cudaSuccess) {
         delete im;
@@ -602,6 +644,9 @@ extern "C" int snes_image_new(snes_ctx *ctx, const uint8_t *rgba, int width, int
     im->dev.cur_err = (double *)(b + o_err);
     im->dev.lab = im->cfg.perceptual_palettes ? (const float *)(b + o_lab) : nullptr;
     im->dev.alpha = (const uint8_t *)(b + o_alpha);
+    im->dev.base_gi = (uint8_t *)(b + o_bgi);
+    im->dev.excl_idx = (uint8_t *)(b + o_xi);
+    im->dev.excl_key = (int *)(b + o_xk);
 
     cudaStream_t st = ctx->stream;
     int rc = SNES_OK;

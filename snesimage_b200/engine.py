@@ -81,7 +81,7 @@ _SIGNATURES = {
     "snes_ctx_set_stream": (_i, [_vp, _vp]),
     "snes_ctx_synchronize": (_i, [_vp]),
     "snes_ctx_set_chunk": (_i, [_vp, _i]),
-    "snes_ctx_set_scorer": (_i, [_vp, _i, _i]),
+    "snes_ctx_set_scorer": (_i, [_vp, _i, _i, _i]),
     "snes_ctx_profile_begin": (_i, [_vp]),
     "snes_ctx_profile_end": (_i, [_vp, _vp, _sz, C.POINTER(_sz)]),
     "snes_image_new": (_i, [_vp, _vp, _i, _i, C.POINTER(_Config), C.POINTER(_vp)]),
@@ -192,8 +192,8 @@ class Context:
     def set_chunk(self, evaluations: int):
         _check(self._l.snes_ctx_set_chunk(self._h, int(evaluations)), "snes_ctx_set_chunk")
 
-    def set_scorer(self, fused: bool = True, block_width: int = 32):
-        _check(self._l.snes_ctx_set_scorer(self._h, int(fused), int(block_width)), "snes_ctx_set_scorer")
+    def set_scorer(self, fused: bool = True, block_width: int = 32, delta_assign: bool = True):
+        _check(self._l.snes_ctx_set_scorer(self._h, int(fused), int(block_width), int(delta_assign)), "snes_ctx_set_scorer")
 
     def profile_begin(self):
         _check(self._l.snes_ctx_profile_begin(self._h), "snes_ctx_profile_begin")
