@@ -36,6 +36,7 @@ C, S = 8, 15
 NIMG, NCAND = 64, 64
 # algorithmic bytes per candidate evaluation (8x15 palettes)
 B_ALG = 3_548_624
+B_S2 = 3_219_560      # scoring share of B_ALG: 65,536 + 8,192 + 3,144,960 + 872
 B_MIN = 403_664
 WORKLOAD = "cfg5: 64 synthetic 256x256 images (V family, seeds 0..63) x 64 random candidates/image/GPU per step, 8x15, RGB, no dither"
 
@@ -175,7 +176,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.01)
 
     def start(self):
         if self.nv:
@@ -283,22 +284,36 @@ def run_ours(args):
     e2e_value = evals_per_step * args.steps / (ms_e2e * 1e-3)
 
     # ---- roofline of the dominant kernel ----
+    # Algorithmic bytes per evaluation: S1 = assignment (source RGBA8 + tile/palette tables +
+    # palette_map write), S2 = scoring (palette_map + alpha mask + 36 B of source planes per scale-pixel + partial sums).
     peak, peak_src = measured_peaks()
+    total_ms = sum(v["ms"] for v in prof.values())
     top = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else (None, {"ms": 0.0, "n": 0})
-    local_evals = args.nimg * args.ncand * args.steps
     roofline = None
     if top[0]:
         name, st = top
-        share = st["ms"] / max(1e-9, sum(v["ms"] for v in prof.values()))
-        # The scorer's scale-0 blur passes each read/write a share of B_ALG; attribute the whole
-        # per-evaluation algorithmic traffic to the pipeline and the kernel's share of pipeline time to it.
-        per_launch_bytes = B_ALG * local_evals / st["n"]
-        achieved = B_ALG * local_evals / (sum(v["ms"] for v in prof.values()) * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                    "kernel": name, "kernel_share_of_gpu_time": share, "kernel_ms_per_launch": st["ms"] / st["n"],
-                    "alg_bytes_per_eval": B_ALG, "alg_bytes_per_launch": per_launch_bytes, "peak_source": peak_src,
-                    "note": "pipeline of several kernels this round: achieved = B_alg x evaluations / summed kernel time (CUDA events per launch)",
-                    "unique_bytes_per_eval": B_MIN, "kernels": prof}
+        # every launch of the scorer covers one chunk of evaluations (bookkeeping error() launches are small ones);
+        # evaluations it processed in the timed region = candidates + the per-step error() of each image
+        scored = (args.nimg * args.ncand + args.nimg) * args.steps
+        alg_bytes = B_S2 if name.startswith("k_score_fused") else B_ALG
+        per_launch_bytes = alg_bytes * scored / st["n"]
+        achieved = alg_bytes * scored / (st["ms"] * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            if tj.get("kernel", "").split("<")[0] == name.split("<")[0]:
+                traffic = tj["dram_bytes_per_eval"] * scored / st["n"]
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "kernel": name, "kernel_launches": st["n"], "kernel_ms_per_launch": st["ms"] / st["n"],
+                    "kernel_share_of_gpu_time": st["ms"] / max(1e-9, total_ms),
+                    "alg_bytes_per_eval": alg_bytes, "alg_bytes_per_launch": per_launch_bytes, "peak_source": peak_src,
+                    "whole_path": {"alg_bytes_per_eval": B_ALG, "achieved": B_ALG * scored / (total_ms * 1e-3) / 1e9,
+                                   "frac": B_ALG * scored / (total_ms * 1e-3) / 1e9 / peak, "gpu_ms_per_step": total_ms / args.steps},
+                    "unique_bytes_per_eval": B_MIN,
+                    "note": "the scorer is FP32/FP64 issue-bound (recursive-Gaussian chains), not HBM-bound: see DESIGN.md for the instruction roofline",
+                    "kernels": prof}
 
     if rank == 0:
         line = {
@@ -327,7 +342,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nimg", type=int, default=NIMG)
     ap.add_argument("--ncand", type=int, default=NCAND)
-    ap.add_argument("--chunk", type=int, default=256)
+    ap.add_argument("--chunk", type=int, default=4096)
     ap.add_argument("--cpu-evals", type=int, default=128)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

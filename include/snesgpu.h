@@ -80,7 +80,7 @@ int snes_ctx_profile_end(snes_ctx *ctx, char *buf, size_t cap, size_t *len);
  *   delta_assign != 0 without dithering, a candidate re-decides only the pixels its entry can change (default)
  * Env overrides at context creation: SNESGPU_FUSED, SNESGPU_BW, SNESGPU_DELTA. */
 int snes_ctx_set_scorer(snes_ctx *ctx, int fused, int block_width, int delta_assign);
-/* how many candidate evaluations have their scratch live at once (default 256, env SNESGPU_CHUNK) */
+/* how many candidate evaluations have their scratch live at once (default 2048, env SNESGPU_CHUNK) */
 int snes_ctx_set_chunk(snes_ctx *ctx, int evaluations);
 
 /* ---- OptimizedImage ------------------------------------------------------------------------- */

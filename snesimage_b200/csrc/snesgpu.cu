@@ -54,13 +54,13 @@ struct snes_ctx {
     int device = 0;
     cudaStream_t own = nullptr, stream = nullptr;
     int64_t launches = 0;
-    int chunk = 256;  // evaluations whose scratch (palette_map, coarse XYB pyramid) is live at once
+    int chunk = 2048;  // evaluations whose scratch (palette_map, coarse XYB pyramid) is live at once
     int fused = 1;    // 1: k_score_fused (on-chip blur planes); 0: multi-kernel pipeline (SNESGPU_FUSED=0)
     int bw = 32;      // column-block width of the fused scorer (16 or 32, SNESGPU_BW)
     int delta = 1;    // 1: no-dither candidates re-decide only the pixels the replaced entry can change (SNESGPU_DELTA)
 
     // per-chunk scratch
-    size_t chunk_cap = 0;
+    size_t chunk_cap = 0, pipe_cap = 0;
     float *xyb_rm = nullptr, *xyb_cm = nullptr, *hbuf = nullptr;
     uint8_t *maps = nullptr;
     // per-batch scratch
@@ -367,21 +367,30 @@ extern "C" int snes_ctx_set_chunk(snes_ctx *ctx, int evaluations) {
 }
 
 // ---- scratch management ------------------------------------------------------------------------
-static int ensure_chunk(snes_ctx *ctx, size_t n) {
-    if (n <= ctx->chunk_cap) return SNES_OK;
-    CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->xyb_rm);
-    cudaFree(ctx->xyb_cm);
-    cudaFree(ctx->hbuf);
-    cudaFree(ctx->maps);
-    ctx->xyb_rm = ctx->xyb_cm = ctx->hbuf = nullptr;
-    ctx->maps = nullptr;
-    ctx->chunk_cap = 0;
-    RET(dev_alloc(&ctx->xyb_rm, n * EVAL_XYB_FLOATS));
-    RET(dev_alloc(&ctx->xyb_cm, n * EVAL_XYB_FLOATS));
-    RET(dev_alloc(&ctx->hbuf, n * EVAL_XYB_FLOATS * 3));
-    RET(dev_alloc(&ctx->maps, n * NPIX));
-    ctx->chunk_cap = n;
+// Scratch of one chunk of evaluations.  The fused path needs only the palette_map (64 KiB) and the coarse XYB
+// pyramid per evaluation; the column-major copy and the H planes exist for the multi-kernel pipeline only.
+static int ensure_chunk(snes_ctx *ctx, size_t n, bool pipeline) {
+    if (n > ctx->chunk_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->xyb_rm);
+        cudaFree(ctx->maps);
+        ctx->xyb_rm = nullptr;
+        ctx->maps = nullptr;
+        ctx->chunk_cap = 0;
+        RET(dev_alloc(&ctx->xyb_rm, n * EVAL_XYB_FLOATS));
+        RET(dev_alloc(&ctx->maps, n * NPIX));
+        ctx->chunk_cap = n;
+    }
+    if (pipeline && n > ctx->pipe_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->xyb_cm);
+        cudaFree(ctx->hbuf);
+        ctx->xyb_cm = ctx->hbuf = nullptr;
+        ctx->pipe_cap = 0;
+        RET(dev_alloc(&ctx->xyb_cm, n * EVAL_XYB_FLOATS));
+        RET(dev_alloc(&ctx->hbuf, n * EVAL_XYB_FLOATS * 3));
+        ctx->pipe_cap = n;
+    }
     return SNES_OK;
 }
 
@@ -466,7 +475,7 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
     cudaStream_t st = ctx->stream;
     RET(ensure_evals(ctx, (size_t)E));
     const int chunk = E < ctx->chunk ? E : ctx->chunk;
-    if (pl.do_score || (pl.do_assign && !pl.self && !pl.d_maps_out)) RET(ensure_chunk(ctx, (size_t)chunk));
+    if (pl.do_score || (pl.do_assign && !pl.self && !pl.d_maps_out)) RET(ensure_chunk(ctx, (size_t)chunk, !ctx->fused));
     const float4 *labtab = cfg.perceptual_palettes ? ctx->labtab : nullptr;
 
     LAUNCH(ctx, "k_tables", k_tables<<<pl.nimg + (pl.ovr >= 0 ? (E + 255) / 256 : 0), 256, 0, st>>>(ctx->d_imgs, pl.nimg, CS, pl.d_cand,
@@ -662,7 +671,7 @@ extern "C" int snes_image_new(snes_ctx *ctx, const uint8_t *rgba, int width, int
         // source side of SSIMULACRA2, once per image: XYB pyramid, mu1 = blur(i1), s11 = blur(i1*i1)
         snes_image *one[1] = {im};
         RET(bind_images(ctx, one, 1));
-        RET(ensure_chunk(ctx, 1));
+        RET(ensure_chunk(ctx, 1, true));
         LAUNCH(ctx, "k_pyramid<true>", k_pyramid<true><<<dim3(16, 1), 256, 0, st>>>(ctx->d_imgs, nullptr, 1, 0, 0, 0, -1, nullptr, 0, nullptr, nullptr, 0, 0));
         for (int s = 0; s < NSCALES; s++) {
             const int d = W >> s, lines = 3 * d;
@@ -830,7 +839,7 @@ extern "C" int snes_image_as_rgba(snes_image *im, uint8_t *out_rgba) {
     if (!im || !out_rgba) return fail(SNES_E_INVALID, "snes_image_as_rgba: NULL argument");
     snes_ctx *ctx = im->ctx;
     RET(set_device(ctx));
-    RET(ensure_chunk(ctx, 1));
+    RET(ensure_chunk(ctx, 1, true));
     uchar4 *tmp = reinterpret_cast<uchar4 *>(ctx->hbuf);
     LAUNCH(ctx, "k_as_rgba", k_as_rgba<<<256, 256, 0, ctx->stream>>>(im->dev, im->cfg.subpalette_size, tmp));
     CK(cudaMemcpyAsync(out_rgba, tmp, NPIX * 4, cudaMemcpyDeviceToHost, ctx->stream));
