@@ -35,16 +35,16 @@ constexpr int FUSED_WARPS = FUSED_THREADS / 32;
 template <int BW>
 struct FusedSmem {
     static constexpr int HB = 128;
-    static constexpr int NCOL = BW + 10;  // 6 halo columns on the left, 4 on the right
-    static constexpr int IP = BW + 11;    // odd pitch: lane = row reads are conflict-free
+    static constexpr int NCOL = BW + 12;  // staged columns c0-8 .. c0+BW+3 (taps reach c0-6 .. c0+BW+3), 16-byte chunks
+    static constexpr int IP = NCOL;       // pitch = 44 floats at BW = 32: lane = row reads are skewed to stay conflict-free
+    static constexpr int NCH = NCOL / 4;
     static constexpr int HP = BW + 1;
-    static constexpr int NW = (BW + 16) / 4;
+    alignas(16) float in2[HB + 4][IP];   // i2 of rows r0-4 .. r0+HB-1 (the 4 extra rows serve the lagging maps)
+    alignas(16) float in1[HB + 4][IP];   // i1 of the same tile
     float hout[3][HB + 10][HP];
-    float in2[HB + 4][IP];   // i2 of rows r0-4 .. r0+HB-1 (the 4 extra rows serve the lagging maps)
-    float in1[HB + 4][IP];   // i1 of the same tile
     float xyb[MAX_ENTRIES + 1];
     double red[FUSED_WARPS][NSUMS];
-    uint32_t raw[HB + 4][NW];   // scale 0: palette_map bytes of the tile, aligned 4-pixel words (columns c0-8 .. c0+BW+7)
+    uint32_t raw[HB + 4][NCH];           // scale 0: palette_map bytes of the tile as aligned 4-pixel words
     uint8_t tp[NTILES];
 };
 
@@ -63,13 +63,18 @@ struct FusedArgs {
 __device__ __forceinline__ void cp_async4(unsigned sdst, const void *gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sdst), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16(unsigned sdst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sdst), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 __device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 // x / y for 1 <= y < 2^100 in f64 without the slow-path checks of the generic division: f32 reciprocal seed,
 // two Newton steps, one residual correction (Markstein).  Correctly rounded except for rare last-bit cases.
 __device__ __forceinline__ double div64_fast(double x, double y) {
-    double r = (double)__frcp_rn((float)y);
+    float rf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)y));   // MUFU.RCP seed, ~2^-23
+    double r = (double)rf;
     double e = fma(-y, r, 1.0);
     r = fma(r, e, r);
     e = fma(-y, r, 1.0);
@@ -85,7 +90,6 @@ __device__ __forceinline__ void fused_scale(SM &sm, const FusedArgs &a, const Im
     constexpr int HB = D < 128 ? D : 128;     // rows per half
     constexpr int NH = D / HB;
     constexpr int NJ = D / BW;
-    constexpr int NCOL = BW + 10;
     constexpr int RPW = 32 / BW;              // rows one warp covers per maps iteration
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const size_t poff = 3 * (size_t)scale_off(scale) + (size_t)ch * D * D;
@@ -97,11 +101,11 @@ __device__ __forceinline__ void fused_scale(SM &sm, const FusedArgs &a, const Im
     const float d1_0 = c_d1[0], d1_1 = c_d1[1], d1_2 = c_d1[2];
     const float md1_0 = -d1_0, md1_1 = -d1_1, md1_2 = -d1_2;
 
-    float hp[NH][3][3], hq[NH][3][3];  // horizontal IIR state of this thread's row(s): prev, prev2
+    float hp[NH][2][3], hq[NH][2][3];  // horizontal IIR state of this thread's row(s) and plane slot(s): prev, prev2
 #pragma unroll
     for (int h = 0; h < NH; h++)
 #pragma unroll
-        for (int p = 0; p < 3; p++)
+        for (int p = 0; p < 2; p++)
 #pragma unroll
             for (int k = 0; k < 3; k++) hp[h][p][k] = hq[h][p][k] = 0.0f;
     double acc[NSUMS] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
@@ -114,52 +118,43 @@ __device__ __forceinline__ void fused_scale(SM &sm, const FusedArgs &a, const Im
             const int r0 = h * HB;
             const int y_lo = r0 - 4 < 0 ? 0 : r0 - 4;        // first staged image row; buffer row = y - (r0 - 4)
             const int nrows = r0 + HB - y_lo;
-            // ---- stage the tile (rows y_lo .. r0+HB-1, columns c0-6 .. c0+BW+3; zero outside the image) ----------
-            // Everything goes global -> smem with 4-byte cp.async, so all of a thread's loads are in flight at once and
-            // cost no registers: i1 (and i2 at scales >= 1) one row per warp iteration, lane = column; at scale 0 the
-            // palette_map bytes as aligned words (two rows per warp iteration), converted after the wait by the thread
-            // that fetched them -- the rendered pixel is a table lookup of its palette entry (as_rgba, lib.rs:550-577).
+            // ---- stage the tile (rows y_lo .. r0+HB-1, columns c0-8 .. c0+BW+3; zero outside the image) ----------
+            // Everything goes global -> smem with cp.async (no registers, all of a thread's loads in flight at once):
+            // i1 (and i2 at scales >= 1) as 16-byte chunks, at scale 0 the palette_map bytes as aligned words that the
+            // fetching thread converts after the wait -- the rendered pixel is a table lookup of its palette entry
+            // (as_rgba, lib.rs:550-577).  A warp iteration covers two rows: lane = (row parity, chunk).
             {
-                const unsigned s_in1 = smem_addr(&sm.in1[0][0]), s_in2 = smem_addr(&sm.in2[0][0]);
                 const int ry_lo = y_lo - (r0 - 4);
-#pragma unroll
-                for (int kk = 0; kk < NCOL; kk += 32) {
-                    const int k = kk + lane, x = c0 - 6 + k;
-                    if (k < NCOL) {
-                        const bool xin = x >= 0 && x < D;
-                        const float *g1 = i1p + (size_t)(y_lo + warp) * D + x;
-                        const float *g2 = i2p + (size_t)(y_lo + warp) * D + x;
-                        unsigned so = ((ry_lo + warp) * SM::IP + k) * 4;
-                        for (int r = warp; r < nrows; r += FUSED_WARPS) {
-                            if (xin) {
-                                cp_async4(s_in1 + so, g1);
-                                if (D != W) cp_async4(s_in2 + so, g2);
-                            } else {
-                                sm.in1[ry_lo + r][k] = 0.0f;
-                                sm.in2[ry_lo + r][k] = 0.0f;
-                            }
-                            g1 += FUSED_WARPS * D;
-                            g2 += FUSED_WARPS * D;
-                            so += FUSED_WARPS * SM::IP * 4;
+                const int w4 = lane & 15, rs = lane >> 4;
+                const int x0 = c0 - 8 + 4 * w4;
+                if (w4 < SM::NCH) {
+                    const bool inside = x0 >= 0 && x0 < D;   // D and x0 are multiples of 4: a chunk is all in or all out
+                    const int rr0 = 2 * warp + rs;
+                    const float *g1 = i1p + (size_t)(y_lo + rr0) * D + x0;
+                    const float *g2 = i2p + (size_t)(y_lo + rr0) * D + x0;
+                    const uint8_t *gm = map + (y_lo + rr0) * W + x0;
+                    unsigned so1 = smem_addr(&sm.in1[ry_lo + rr0][4 * w4]);
+                    unsigned so2 = smem_addr(&sm.in2[ry_lo + rr0][4 * w4]);
+                    unsigned sor = smem_addr(&sm.raw[ry_lo + rr0][w4]);
+                    for (int r = rr0; r < nrows; r += 2 * FUSED_WARPS) {
+                        if (inside) {
+                            cp_async16(so1, g1);
+                            if (D != W) cp_async16(so2, g2);
+                            else cp_async4(sor, gm);
+                        } else {
+                            *reinterpret_cast<float4 *>(&sm.in1[ry_lo + r][4 * w4]) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                            *reinterpret_cast<float4 *>(&sm.in2[ry_lo + r][4 * w4]) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                         }
+                        g1 += 2 * FUSED_WARPS * D;
+                        g2 += 2 * FUSED_WARPS * D;
+                        gm += 2 * FUSED_WARPS * W;
+                        so1 += 2 * FUSED_WARPS * SM::IP * 4;
+                        so2 += 2 * FUSED_WARPS * SM::IP * 4;
+                        sor += 2 * FUSED_WARPS * SM::NCH * 4;
                     }
-                }
-                if (D == W) {
-                    const int w4 = lane & 15, rs = lane >> 4;      // word within the row, row parity
-                    const int x0 = c0 - 8 + 4 * w4;
-                    const bool win = w4 < SM::NW && x0 >= 0 && x0 < D;
-                    if (win) {
-                        const uint8_t *gm = map + (y_lo + 2 * warp + rs) * W + x0;
-                        unsigned so = smem_addr(&sm.raw[ry_lo + 2 * warp + rs][w4]);
-                        for (int r = 2 * warp + rs; r < nrows; r += 2 * FUSED_WARPS) {
-                            cp_async4(so, gm);
-                            gm += 2 * FUSED_WARPS * W;
-                            so += 2 * FUSED_WARPS * SM::NW * 4;
-                        }
-                    }
-                    cp_async_wait_all();
-                    if (win) {
-                        for (int r = 2 * warp + rs; r < nrows; r += 2 * FUSED_WARPS) {
+                    if (D == W && inside) {
+                        cp_async_wait_all();
+                        for (int r = rr0; r < nrows; r += 2 * FUSED_WARPS) {
                             const int y = y_lo + r, ry = ry_lo + r;
                             const uint32_t mw = sm.raw[ry][w4];
                             uint32_t aw = 0xffffffffu;
@@ -168,53 +163,71 @@ __device__ __forceinline__ void fused_scale(SM &sm, const FusedArgs &a, const Im
                                 aw = __ldg(reinterpret_cast<const uint32_t *>(im.alpha + y * W + x0));
                                 sub = sm.tp[(y >> 3) * 32 + (x0 >> 3)];
                             }
-#pragma unroll
-                            for (int i = 0; i < 4; i++) {
-                                const int k = 4 * w4 - 2 + i;
-                                if (k >= 0 && k < NCOL) {
-                                    const int gi = ((aw >> (8 * i)) & 255) ? sub + ((mw >> (8 * i)) & 255) : BLACK;
-                                    sm.in2[ry][k] = sm.xyb[gi];
-                                }
-                            }
+                            float4 v;
+                            v.x = sm.xyb[(aw & 255u) ? sub + (mw & 255u) : BLACK];
+                            v.y = sm.xyb[((aw >> 8) & 255u) ? sub + ((mw >> 8) & 255u) : BLACK];
+                            v.z = sm.xyb[((aw >> 16) & 255u) ? sub + ((mw >> 16) & 255u) : BLACK];
+                            v.w = sm.xyb[(aw >> 24) ? sub + (mw >> 24) : BLACK];
+                            *reinterpret_cast<float4 *>(&sm.in2[ry][4 * w4]) = v;
                         }
                     }
                 }
             }
             cp_async_wait_all();
             __syncthreads();
-            // ---- horizontal pass: thread = row r0 + t ---------------------------------------------------------------
-            if (t < HB) {
-                const float *r2 = sm.in2[t + 4], *r1 = sm.in1[t + 4];
-                auto hstep = [&](float s0, float s1, float s2, int store_col) {
-                    const float sum[3] = {s0, s1, s2};
-#pragma unroll
-                    for (int p = 0; p < 3; p++) {
-                        float o0 = sum[p] * n2_0 - hq[h][p][0];
-                        float o1 = sum[p] * n2_1 - hq[h][p][1];
-                        float o2 = sum[p] * n2_2 - hq[h][p][2];
-                        o0 = __fmaf_rn(md1_0, hp[h][p][0], o0);
-                        o1 = __fmaf_rn(md1_1, hp[h][p][1], o1);
-                        o2 = __fmaf_rn(md1_2, hp[h][p][2], o2);
-                        hq[h][p][0] = hp[h][p][0];
-                        hq[h][p][1] = hp[h][p][1];
-                        hq[h][p][2] = hp[h][p][2];
-                        hp[h][p][0] = o0;
-                        hp[h][p][1] = o1;
-                        hp[h][p][2] = o2;
-                        if (store_col >= 0) sm.hout[p][10 + t][store_col] = (o0 + o1) + o2;
-                    }
+            // ---- horizontal pass: thread = (row r0 + (t & 127), plane group t >> 7) -------------------------------------
+            // group 0 (warps 0-3) runs the planes {i2, i2*i2}, group 1 (warps 4-7) the plane {i1*i2}: all 8 warps busy.
+            // The 16-byte staging forces an even row pitch, so lanes (= rows) are skewed by (row >> 3) & 3 columns:
+            // bank = 44*row + column is then distinct across the warp.  Tap columns in the tile: n-6 -> q+2, n+4 -> q+12.
+            if ((t & 127) < HB) {
+                const int row = t & 127, skew = (row >> 3) & 3;
+                const float *r2 = sm.in2[row + 4], *r1 = sm.in1[row + 4];
+                auto section = [&](float sum, int p) {   // p = plane slot of this thread's state
+                    float o0 = sum * n2_0 - hq[h][p][0];
+                    float o1 = sum * n2_1 - hq[h][p][1];
+                    float o2 = sum * n2_2 - hq[h][p][2];
+                    o0 = __fmaf_rn(md1_0, hp[h][p][0], o0);
+                    o1 = __fmaf_rn(md1_1, hp[h][p][1], o1);
+                    o2 = __fmaf_rn(md1_2, hp[h][p][2], o2);
+                    hq[h][p][0] = hp[h][p][0];
+                    hq[h][p][1] = hp[h][p][1];
+                    hq[h][p][2] = hp[h][p][2];
+                    hp[h][p][0] = o0;
+                    hp[h][p][1] = o1;
+                    hp[h][p][2] = o2;
+                    return (o0 + o1) + o2;
                 };
-                if (j == 0) {  // warm-up n = -4..-1: left taps are outside the image
+                if (t < 128) {
+                    if (j == 0) {  // warm-up n = -4..-1: left taps are outside the image
 #pragma unroll
-                    for (int n = -4; n < 0; n++) {
-                        const float ar = r2[n + 10], br = r1[n + 10];
-                        hstep(ar, ar * ar, br * ar, -1);
+                        for (int n = -4; n < 0; n++) {
+                            const float ar = r2[n + 12];
+                            section(ar, 0);
+                            section(ar * ar, 1);
+                        }
                     }
-                }
 #pragma unroll 4
-                for (int q = 0; q < BW; q++) {  // n = c0 + q: right tap column n+4 -> k = q+10, left tap n-6 -> k = q
-                    const float ar = r2[q + 10], al = r2[q], br = r1[q + 10], bl = r1[q];
-                    hstep(al + ar, al * al + ar * ar, bl * al + br * ar, q);
+                    for (int qq = 0; qq < BW + 3; qq++) {  // n = c0 + q
+                        const int q = qq - skew;
+                        if (q >= 0 && q < BW) {
+                            const float ar = r2[q + 12], al = r2[q + 2];
+                            sm.hout[0][10 + row][q] = section(al + ar, 0);
+                            sm.hout[1][10 + row][q] = section(al * al + ar * ar, 1);
+                        }
+                    }
+                } else {
+                    if (j == 0) {
+#pragma unroll
+                        for (int n = -4; n < 0; n++) section(r1[n + 12] * r2[n + 12], 0);
+                    }
+#pragma unroll 4
+                    for (int qq = 0; qq < BW + 3; qq++) {
+                        const int q = qq - skew;
+                        if (q >= 0 && q < BW) {
+                            const float ar = r2[q + 12], al = r2[q + 2], br = r1[q + 12], bl = r1[q + 2];
+                            sm.hout[2][10 + row][q] = section(bl * al + br * ar, 0);
+                        }
+                    }
                 }
             }
             __syncthreads();
@@ -278,7 +291,7 @@ __device__ __forceinline__ void fused_scale(SM &sm, const FusedArgs &a, const Im
                         if (n < n_end) {
                             const int bi = n - r0 + 4;
                             const float mu2 = sm.hout[0][bi][col], s22 = sm.hout[1][bi][col], s12 = sm.hout[2][bi][col];
-                            const float i1 = sm.in1[bi][col + 6], i2 = sm.in2[bi][col + 6];
+                            const float i1 = sm.in1[bi][col + 8], i2 = sm.in2[bi][col + 8];
                             const float mu1 = mu1v[u], s11 = s11v[u];
                             const float mu11 = mu1 * mu1, mu22 = mu2 * mu2, mu12 = mu1 * mu2;
                             const float mu_diff = mu1 - mu2;

@@ -337,3 +337,46 @@ def test_scorer_variants_agree(ctx):
     assert np.array_equal(got["fused32"], got["fused32full"])   # delta assignment changes no decision
     assert np.max(np.abs(got["fused32"] - got["pipeline"])) <= 1e-10
     assert np.max(np.abs(got["fused16"] - got["pipeline"])) <= 1e-10
+
+
+def test_sharded_argmin_matches_single_rank(ctx):
+    """The candidate-sharded step of driver.BatchOptimizer, with the ranks emulated one after the other on one GPU:
+    slice evaluation -> gathered (err, idx) records -> k_merge_best -> k_apply_best must equal the unsharded step."""
+    import torch
+    from snesimage_b200 import driver
+    C, S, nimg, ncand, world = 4, 7, 3, 24, 3
+    cfg = engine.Config(subpalette_count=C, subpalette_size=S)
+    imgs = [engine.OptimizedImage(ctx, synth.image(90 + j, "V"), cfg) for j in range(nimg)]
+    twins = [engine.OptimizedImage(ctx, synth.image(90 + j, "V"), cfg) for j in range(nimg)]
+    for group in (imgs, twins):
+        engine.batch_initialize_tiles(group)
+        engine.batch_recalculate_palettes(group)
+    cand = np.stack([synth.candidates(90 + j, 0, ncand) for j in range(nimg)])
+    cand[:, 20] = cand[:, 4]   # an exact tie across two different shards: the lower index must win
+    ref = engine.batch_eval_candidates(imgs, 1, 2, cand)
+    dev = torch.device("cuda", 0)
+    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream or 1)
+    try:
+        d_cand = torch.from_numpy(cand).to(dev)
+        gathered = torch.zeros(world * nimg * 2, dtype=torch.int64, device=dev)
+        merged = torch.zeros(nimg * 2, dtype=torch.int64, device=dev)
+        engine.batch_error_dev(imgs)
+        for r in range(world):
+            lo, hi = driver.shard_bounds(ncand, r, world)
+            sl = d_cand[:, lo:hi, :].contiguous()
+            engine.batch_eval_candidates_dev(imgs, 1, 2, sl.data_ptr(), hi - lo, lo, None,
+                                             gathered.data_ptr() + r * nimg * 16)
+        engine.merge_best_dev(ctx, gathered.data_ptr(), world, nimg, merged.data_ptr())
+        engine.batch_apply_best_dev(imgs, 1, 2, d_cand.data_ptr(), ncand, merged.data_ptr())
+        torch.cuda.synchronize()
+        got = merged.cpu().numpy().view(engine.BEST_DTYPE)
+    finally:
+        ctx.set_stream(None)
+    assert np.array_equal(got["idx"], ref["best"]["idx"])
+    assert np.array_equal(got["err"], ref["best"]["err"])
+    engine.batch_step_random(twins, 1, 2, cand)
+    for a, b in zip(imgs, twins):
+        assert np.array_equal(a.palette, b.palette)
+        assert np.array_equal(a.palette_map, b.palette_map)
+    for im in imgs + twins:
+        im.close()
