@@ -56,6 +56,7 @@ struct ImgDev {
     const float *xyb_cm;      // same, transposed [scale][ch][x][y]
     float *mu1;               // blur(i1)       [scale][ch][y][x]
     float *s11;               // blur(i1*i1)    [scale][ch][y][x]
+    float2 *ms11;             // (mu1, s11) interleaved, same index space (read by k_score_v2's maps)
     PalTables *tables;
     double *cur_err;          // error() of the current state
     const float *lab;         // per-pixel Lab of the original (perceptual mode), [NPIX][4]

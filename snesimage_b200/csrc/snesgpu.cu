@@ -18,6 +18,7 @@
 #include "kmeans.cuh"
 #include "lab.cuh"
 #include "score_fused.cuh"
+#include "score_v2.cuh"
 #include "assign_delta.cuh"
 
 using namespace snes;
@@ -55,7 +56,7 @@ struct snes_ctx {
     cudaStream_t own = nullptr, stream = nullptr;
     int64_t launches = 0;
     int chunk = 2048;  // evaluations whose scratch (palette_map, coarse XYB pyramid) is live at once
-    int fused = 1;    // 1: k_score_fused (on-chip blur planes); 0: multi-kernel pipeline (SNESGPU_FUSED=0)
+    int fused = 2;    // 2: k_score_v2 (packed-f32 fused scorer); 1: k_score_fused; 0: multi-kernel pipeline (SNESGPU_FUSED)
     int bw = 32;      // column-block width of the fused scorer (16 or 32, SNESGPU_BW)
     int delta = 1;    // 1: no-dither candidates re-decide only the pixels the replaced entry can change (SNESGPU_DELTA)
 
@@ -225,7 +226,7 @@ extern "C" int snes_ctx_create(int device, snes_ctx **out) {
         if (v > 0) ctx->chunk = v;
     }
 
-    if (const char *c = getenv("SNESGPU_FUSED")) ctx->fused = atoi(c) != 0;
+    if (const char *c = getenv("SNESGPU_FUSED")) ctx->fused = atoi(c) < 0 ? 0 : (atoi(c) > 2 ? 2 : atoi(c));
     if (const char *c = getenv("SNESGPU_BW")) ctx->bw = atoi(c) == 16 ? 16 : 32;
     if (const char *c = getenv("SNESGPU_DELTA")) ctx->delta = atoi(c) != 0;
 
@@ -247,12 +248,29 @@ extern "C" int snes_ctx_create(int device, snes_ctx **out) {
     CK(cudaMemcpyToSymbol(c_srgb_lin_lut, lut2, sizeof(lut2)));
     CK(cudaMemcpyToSymbol(c_n2, n2, sizeof(n2)));
     CK(cudaMemcpyToSymbol(c_d1, d1, sizeof(d1)));
+    {
+        float2 n2p[3], d1p[3], md1p[3];
+        float md1[3];
+        for (int k = 0; k < 3; k++) {
+            n2p[k] = make_float2(n2[k], n2[k]);
+            d1p[k] = make_float2(d1[k], d1[k]);
+            md1p[k] = make_float2(-d1[k], -d1[k]);
+            md1[k] = -d1[k];
+        }
+        CK(cudaMemcpyToSymbol(c_n2p, n2p, sizeof(n2p)));
+        CK(cudaMemcpyToSymbol(c_d1p, d1p, sizeof(d1p)));
+        CK(cudaMemcpyToSymbol(c_md1p, md1p, sizeof(md1p)));
+        CK(cudaMemcpyToSymbol(c_md1, md1, sizeof(md1)));
+        const float2 m1p = make_float2(-1.0f, -1.0f);
+        CK(cudaMemcpyToSymbol(c_m1p, &m1p, sizeof(m1p)));
+    }
     CK(cudaMemcpyToSymbol(c_weight, kWeights, sizeof(kWeights)));
     CK(cudaMemcpyToSymbol(c_nes, nes4, sizeof(nes4)));
     CK(cudaFuncSetAttribute(k_blur_h<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlurHSmem0));
     CK(cudaFuncSetAttribute(k_blur_h<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlurHSmem1));
     CK(cudaFuncSetAttribute(k_score_fused<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<32>)));
     CK(cudaFuncSetAttribute(k_score_fused<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<16>)));
+    CK(cudaFuncSetAttribute(k_score_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V2Smem)));
 
     RET(dev_alloc(&ctx->labtab, 32768));
     LAUNCH(ctx, "k_build_lab_table", k_build_lab_table<<<128, 256, 0, ctx->stream>>>(ctx->labtab));
@@ -354,7 +372,7 @@ extern "C" int snes_ctx_profile_end(snes_ctx *ctx, char *buf, size_t cap, size_t
 
 extern "C" int snes_ctx_set_scorer(snes_ctx *ctx, int fused, int block_width, int delta_assign) {
     if (!ctx || (block_width != 16 && block_width != 32)) return fail(SNES_E_INVALID, "snes_ctx_set_scorer: bad argument");
-    ctx->fused = fused != 0;
+    ctx->fused = fused < 0 ? 0 : (fused > 2 ? 2 : fused);
     ctx->bw = block_width;
     ctx->delta = delta_assign != 0;
     return SNES_OK;
@@ -469,6 +487,17 @@ struct EvalPlan {
     double *d_scores = nullptr;       // [E] device output of do_score
 };
 
+static int launch_scorer(snes_ctx *ctx, const FusedArgs &fa, int ec) {
+    cudaStream_t st = ctx->stream;
+    if (ctx->fused == 2)
+        LAUNCH(ctx, "k_score_v2", k_score_v2<<<dim3(3, ec), V2_THREADS, sizeof(V2Smem), st>>>(fa));
+    else if (ctx->bw == 16)
+        LAUNCH(ctx, "k_score_fused<16>", k_score_fused<16><<<dim3(3, ec), FUSED_THREADS, sizeof(FusedSmem<16>), st>>>(fa));
+    else
+        LAUNCH(ctx, "k_score_fused<32>", k_score_fused<32><<<dim3(3, ec), FUSED_THREADS, sizeof(FusedSmem<32>), st>>>(fa));
+    return SNES_OK;
+}
+
 // Requires bind_images() first.
 static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
     const int E = pl.nimg * pl.ncand, S = cfg.subpalette_size, CS = cfg.subpalette_count * cfg.subpalette_size;
@@ -512,10 +541,7 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
             fa.gi_fmt = 1;
             fa.xyb_rm = ctx->xyb_rm;
             fa.partials = ctx->partials;
-            if (ctx->bw == 16)
-                LAUNCH(ctx, "k_score_fused<16>", k_score_fused<16><<<dim3(3, ec), FUSED_THREADS, sizeof(FusedSmem<16>), st>>>(fa));
-            else
-                LAUNCH(ctx, "k_score_fused<32>", k_score_fused<32><<<dim3(3, ec), FUSED_THREADS, sizeof(FusedSmem<32>), st>>>(fa));
+            RET(launch_scorer(ctx, fa, ec));
             continue;
         }
         // scratch maps feed only the fused scorer: write global entry indices (no tile_palettes / alpha lookups later)
@@ -551,10 +577,7 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
             fa.gi_fmt = gi;
             fa.xyb_rm = ctx->xyb_rm;
             fa.partials = ctx->partials;
-            if (ctx->bw == 16)
-                LAUNCH(ctx, "k_score_fused<16>", k_score_fused<16><<<dim3(3, ec), FUSED_THREADS, sizeof(FusedSmem<16>), st>>>(fa));
-            else
-                LAUNCH(ctx, "k_score_fused<32>", k_score_fused<32><<<dim3(3, ec), FUSED_THREADS, sizeof(FusedSmem<32>), st>>>(fa));
+            RET(launch_scorer(ctx, fa, ec));
             continue;
         }
         LAUNCH(ctx, "k_pyramid<false>", k_pyramid<false><<<dim3(16, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self,
@@ -630,7 +653,7 @@ extern "C" int snes_image_new(snes_ctx *ctx, const uint8_t *rgba, int width, int
         return o;
     };
     const size_t o_rgba = take(NPIX * 4), o_tp = take(NTILES), o_pal = take(MAX_ENTRIES * 3), o_map = take(NPIX);
-    const size_t o_rm = take(plane), o_cm = take(plane), o_mu = take(plane), o_s11 = take(plane);
+    const size_t o_rm = take(plane), o_cm = take(plane), o_mu = take(plane), o_s11 = take(plane), o_ms = take(2 * plane);
     const size_t o_tab = take(sizeof(PalTables)), o_err = take(sizeof(double));
     const size_t o_lab = take(im->cfg.perceptual_palettes ? sizeof(float4) * NPIX : 0);
     const size_t o_alpha = take(NPIX);
@@ -649,6 +672,7 @@ extern "C" int snes_image_new(snes_ctx *ctx, const uint8_t *rgba, int width, int
     im->dev.xyb_cm = (const float *)(b + o_cm);
     im->dev.mu1 = (float *)(b + o_mu);
     im->dev.s11 = (float *)(b + o_s11);
+    im->dev.ms11 = (float2 *)(b + o_ms);
     im->dev.tables = (PalTables *)(b + o_tab);
     im->dev.cur_err = (double *)(b + o_err);
     im->dev.lab = im->cfg.perceptual_palettes ? (const float *)(b + o_lab) : nullptr;
@@ -678,6 +702,7 @@ extern "C" int snes_image_new(snes_ctx *ctx, const uint8_t *rgba, int width, int
             LAUNCH(ctx, "k_blur_h<1>", k_blur_h<1><<<(lines + 127) / 128, 128, kBlurHSmem1, st>>>(s, lines, ctx->d_imgs, 1, 0, nullptr, ctx->hbuf));
             LAUNCH(ctx, "k_blur_v<1>", k_blur_v<1><<<(lines + 127) / 128, 128, 0, st>>>(s, lines, ctx->d_imgs, 1, 0, nullptr, ctx->hbuf, nullptr));
         }
+        LAUNCH(ctx, "k_interleave_ms", k_interleave_ms<<<(EVAL_XYB_FLOATS + 255) / 256, 256, 0, st>>>(im->dev.mu1, im->dev.s11, im->dev.ms11, EVAL_XYB_FLOATS));
         CK(cudaStreamSynchronize(st));
         return SNES_OK;
     };
@@ -1228,3 +1253,15 @@ extern "C" int snes_image_kmeans_debug(snes_image *im, double *centres /* 256*3 
     if (status) RET(d2h(im, status, im->km.status, sizeof(int) * 512));
     return SNES_OK;
 }
+
+#ifdef SNES_V2_TIMING
+extern "C" int snes_debug_v2_timing(unsigned long long *out16, int reset) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out16, snes::g_v2_timing, sizeof(unsigned long long) * 16) != cudaSuccess) return -2;
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(snes::g_v2_timing, z, sizeof z);
+    }
+    return 0;
+}
+#endif

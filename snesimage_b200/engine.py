@@ -130,9 +130,10 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_build.SO):
+    so = os.environ.get("SNESGPU_SO") or _build.SO   # SNESGPU_SO: an instrumented debug build (scripts/phase_timing.py)
+    if so == _build.SO and not os.path.exists(so):
         _build.build_library()
-    L = C.CDLL(_build.SO)
+    L = C.CDLL(so)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(L, name)  # AttributeError if the library does not export what the header declares
         fn.restype = res
@@ -192,7 +193,8 @@ class Context:
     def set_chunk(self, evaluations: int):
         _check(self._l.snes_ctx_set_chunk(self._h, int(evaluations)), "snes_ctx_set_chunk")
 
-    def set_scorer(self, fused: bool = True, block_width: int = 32, delta_assign: bool = True):
+    def set_scorer(self, fused: int = 2, block_width: int = 32, delta_assign: bool = True):
+        """fused: 2 = k_score_v2 (default), 1 = k_score_fused, 0 = multi-kernel pipeline (A/B checks)."""
         _check(self._l.snes_ctx_set_scorer(self._h, int(fused), int(block_width), int(delta_assign)), "snes_ctx_set_scorer")
 
     def profile_begin(self):
