@@ -19,6 +19,7 @@
 #include "lab.cuh"
 #include "score_fused.cuh"
 #include "score_v2.cuh"
+#include "score_v3.cuh"
 #include "assign_delta.cuh"
 
 using namespace snes;
@@ -56,7 +57,10 @@ struct snes_ctx {
     cudaStream_t own = nullptr, stream = nullptr;
     int64_t launches = 0;
     int chunk = 2048;  // evaluations whose scratch (palette_map, coarse XYB pyramid) is live at once
-    int fused = 2;    // 2: k_score_v2 (packed-f32 fused scorer); 1: k_score_fused; 0: multi-kernel pipeline (SNESGPU_FUSED)
+    int fused = 3;    // 3: k_score_v3 (persistent 4-warp CTAs); 2: k_score_v2; 1: k_score_fused; 0: multi-kernel pipeline (SNESGPU_FUSED)
+    int nsm = 148;
+    int *v3_counter = nullptr;
+    float *v3_scratch = nullptr;
     int bw = 32;      // column-block width of the fused scorer (16 or 32, SNESGPU_BW)
     int delta = 1;    // 1: no-dither candidates re-decide only the pixels the replaced entry can change (SNESGPU_DELTA)
 
@@ -226,7 +230,7 @@ extern "C" int snes_ctx_create(int device, snes_ctx **out) {
         if (v > 0) ctx->chunk = v;
     }
 
-    if (const char *c = getenv("SNESGPU_FUSED")) ctx->fused = atoi(c) < 0 ? 0 : (atoi(c) > 2 ? 2 : atoi(c));
+    if (const char *c = getenv("SNESGPU_FUSED")) ctx->fused = atoi(c) < 0 ? 0 : (atoi(c) > 3 ? 3 : atoi(c));
     if (const char *c = getenv("SNESGPU_BW")) ctx->bw = atoi(c) == 16 ? 16 : 32;
     if (const char *c = getenv("SNESGPU_DELTA")) ctx->delta = atoi(c) != 0;
 
@@ -271,6 +275,11 @@ extern "C" int snes_ctx_create(int device, snes_ctx **out) {
     CK(cudaFuncSetAttribute(k_score_fused<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<32>)));
     CK(cudaFuncSetAttribute(k_score_fused<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<16>)));
     CK(cudaFuncSetAttribute(k_score_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V2Smem)));
+    CK(cudaFuncSetAttribute(k_score_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V3Smem)));
+    CK(cudaFuncSetAttribute(k_score_v3, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    ctx->nsm = prop.multiProcessorCount;
+    RET(dev_alloc(&ctx->v3_counter, 1));
+    RET(dev_alloc(&ctx->v3_scratch, (size_t)ctx->nsm * V3_CTAS_PER_SM * V3_HSCRATCH_FLOATS));
 
     RET(dev_alloc(&ctx->labtab, 32768));
     LAUNCH(ctx, "k_build_lab_table", k_build_lab_table<<<128, 256, 0, ctx->stream>>>(ctx->labtab));
@@ -300,6 +309,8 @@ extern "C" void snes_ctx_destroy(snes_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     free_scratch(ctx);
     cudaFree(ctx->labtab);
+    cudaFree(ctx->v3_counter);
+    cudaFree(ctx->v3_scratch);
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->own);
     delete ctx;
@@ -372,7 +383,7 @@ extern "C" int snes_ctx_profile_end(snes_ctx *ctx, char *buf, size_t cap, size_t
 
 extern "C" int snes_ctx_set_scorer(snes_ctx *ctx, int fused, int block_width, int delta_assign) {
     if (!ctx || (block_width != 16 && block_width != 32)) return fail(SNES_E_INVALID, "snes_ctx_set_scorer: bad argument");
-    ctx->fused = fused < 0 ? 0 : (fused > 2 ? 2 : fused);
+    ctx->fused = fused < 0 ? 0 : (fused > 3 ? 3 : fused);
     ctx->bw = block_width;
     ctx->delta = delta_assign != 0;
     return SNES_OK;
@@ -489,7 +500,16 @@ struct EvalPlan {
 
 static int launch_scorer(snes_ctx *ctx, const FusedArgs &fa, int ec) {
     cudaStream_t st = ctx->stream;
-    if (ctx->fused == 2)
+    if (ctx->fused == 3) {
+        V3Args va;
+        va.f = fa;
+        va.nitems = 3 * ec;
+        va.counter = ctx->v3_counter;
+        va.hscratch = ctx->v3_scratch;
+        const int grid = va.nitems < ctx->nsm * V3_CTAS_PER_SM ? va.nitems : ctx->nsm * V3_CTAS_PER_SM;
+        CK(cudaMemsetAsync(ctx->v3_counter, 0, sizeof(int), st));
+        LAUNCH(ctx, "k_score_v3", k_score_v3<<<grid, V3_THREADS, sizeof(V3Smem), st>>>(va));
+    } else if (ctx->fused == 2)
         LAUNCH(ctx, "k_score_v2", k_score_v2<<<dim3(3, ec), V2_THREADS, sizeof(V2Smem), st>>>(fa));
     else if (ctx->bw == 16)
         LAUNCH(ctx, "k_score_fused<16>", k_score_fused<16><<<dim3(3, ec), FUSED_THREADS, sizeof(FusedSmem<16>), st>>>(fa));

@@ -193,8 +193,8 @@ class Context:
     def set_chunk(self, evaluations: int):
         _check(self._l.snes_ctx_set_chunk(self._h, int(evaluations)), "snes_ctx_set_chunk")
 
-    def set_scorer(self, fused: int = 2, block_width: int = 32, delta_assign: bool = True):
-        """fused: 2 = k_score_v2 (default), 1 = k_score_fused, 0 = multi-kernel pipeline (A/B checks)."""
+    def set_scorer(self, fused: int = 3, block_width: int = 32, delta_assign: bool = True):
+        """fused: 3 = k_score_v3 (default), 2 = k_score_v2, 1 = k_score_fused, 0 = multi-kernel pipeline (A/B checks)."""
         _check(self._l.snes_ctx_set_scorer(self._h, int(fused), int(block_width), int(delta_assign)), "snes_ctx_set_scorer")
 
     def profile_begin(self):

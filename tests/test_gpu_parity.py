@@ -327,13 +327,15 @@ def test_scorer_variants_agree(ctx):
     want = o.eval_candidates(3, 4, cand)
     got = {}
     try:
-        for name, (fused, bw, delta) in {"v2": (2, 32, True), "v2full": (2, 32, False), "fused32": (1, 32, True), "fused16": (1, 16, True),
+        for name, (fused, bw, delta) in {"v3": (3, 32, True), "v3full": (3, 32, False), "v2": (2, 32, True), "v2full": (2, 32, False), "fused32": (1, 32, True), "fused16": (1, 16, True),
                                          "fused32full": (1, 32, False), "pipeline": (0, 32, False)}.items():
             ctx.set_scorer(fused, bw, delta)
             got[name] = g.eval_candidates(3, 4, cand)
             assert np.max(np.abs(got[name] - want)) <= TIGHT_TOL, name
     finally:
-        ctx.set_scorer(2, 32, True)
+        ctx.set_scorer(3, 32, True)
+    assert np.array_equal(got["v3"], got["v3full"])
+    assert np.max(np.abs(got["v3"] - got["pipeline"])) <= 1e-10
     assert np.array_equal(got["v2"], got["v2full"])
     assert np.max(np.abs(got["v2"] - got["pipeline"])) <= 1e-10
     assert np.array_equal(got["fused32"], got["fused32full"])   # delta assignment changes no decision
