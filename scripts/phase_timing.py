@@ -26,9 +26,9 @@ engine.batch_eval_candidates(imgs, 0, 0, cand, want_scores=False)
 L.snes_debug_v2_timing(buf, 1)
 v = np.array(list(buf), dtype=np.float64)
 ctas = nimg * ncand * 3
-names = ["stage", "H", "V warp busy", "maps warp busy", "V+maps phase"]
+names = ["stage", "H", "V", "maps"] if engine.os.environ.get("SNESGPU_FUSED", "3") == "3" else ["stage", "H", "V warp busy", "maps warp busy", "V+maps phase"]
 for base, label in ((0, "scale 0"), (8, "scales 1-5")):
-    tot = v[base] + v[base + 1] + v[base + 4]
+    tot = v[base] + v[base + 1] + (v[base + 2] + v[base + 3] if len(names) == 4 else v[base + 4])
     print(f"{label}: cycles per CTA {tot / ctas:10.0f}")
     for i, n in enumerate(names):
         print(f"   {n:16s} {v[base + i] / ctas:10.0f}  ({100 * v[base + i] / tot:5.1f}%)")
