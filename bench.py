@@ -295,7 +295,7 @@ def run_ours(args):
         # every launch of the scorer covers one chunk of evaluations (bookkeeping error() launches are small ones);
         # evaluations it processed in the timed region = candidates + the per-step error() of each image
         scored = (args.nimg * args.ncand + args.nimg) * args.steps
-        alg_bytes = B_S2 if name.startswith("k_score_fused") else B_ALG
+        alg_bytes = B_S2 if name.startswith("k_score") else B_ALG
         per_launch_bytes = alg_bytes * scored / st["n"]
         achieved = alg_bytes * scored / (st["ms"] * 1e-3) / 1e9
         traffic = None
