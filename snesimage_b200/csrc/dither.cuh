@@ -18,57 +18,80 @@
 
 namespace snes {
 
+constexpr int DITHER_THREADS = 128;
+
+// grid = evaluations, block = DITHER_THREADS.  Thread i owns row i and then row i + 128: in wavefront time
+// tau = t - 2i it handles pixel x = tau of row i for tau in [0, 255] and pixel x = tau - 256 of row i + 128 for tau in
+// [256, 511] -- the second row starts exactly when the first one ends, so a thread is busy for 512 of the 766 steps
+// (a thread-per-row block would be busy for 256).  The row above the thread's current row is always the current row
+// of thread i - 1 (thread 127 for the first pixel of row 128), so the mailbox is indexed by thread.
 template <bool LAB>
-__global__ void __launch_bounds__(256) k_assign_dither(const ImgDev *imgs, const CandEntry *cents, int ncand, int e0, int S,
-                                                       int CS, int ovr, uint8_t *maps, int to_image, int gi_fmt) {
-    __shared__ uchar4 pal[MAX_ENTRIES];
+__global__ void __launch_bounds__(DITHER_THREADS) k_assign_dither(const ImgDev *imgs, const CandEntry *cents, int ncand, int e0, int S,
+                                                                  int CS, int ovr, uint8_t *maps, int to_image, int gi_fmt) {
+    __shared__ int4 pal[MAX_ENTRIES];  // r, g, b of as_rgba(entry), 1024 + r
     __shared__ float4 pal_lab[LAB ? MAX_ENTRIES : 1];
-    __shared__ double mail[2][H][3];
-    const int e = blockIdx.x, ea = e0 + e, img = ea / ncand, y = threadIdx.x;
+    __shared__ uint8_t s_tp[NTILES];   // tile_palettes * S
+    __shared__ double mail[2][DITHER_THREADS][3];
+    const int e = blockIdx.x, ea = e0 + e, img = ea / ncand, i = threadIdx.x;
     const ImgDev im = imgs[img];
-    for (int j = y; j < CS; j += 256) {
-        pal[j] = (j == ovr) ? cents[ea].rgb8 : im.tables->rgb8[j];
+    for (int j = i; j < CS; j += DITHER_THREADS) {
+        const uchar4 c = (j == ovr) ? cents[ea].rgb8 : im.tables->rgb8[j];
+        pal[j] = make_int4(c.x, c.y, c.z, 1024 + c.x);
         if (LAB) {
             const float *l = (j == ovr) ? cents[ea].lab : im.tables->lab[j];
             pal_lab[j] = make_float4(l[0], l[1], l[2], 0.0f);
         }
     }
-    for (int c = 0; c < 3; c++) mail[0][y][c] = mail[1][y][c] = 0.0;
+    for (int j = i; j < NTILES; j += DITHER_THREADS) s_tp[j] = (uint8_t)(im.tile_pal[j] * S);
+    for (int c = 0; c < 3; c++) mail[0][i][c] = mail[1][i][c] = 0.0;
     __syncthreads();
 
     const double w_e = 7.0 / 16.0, w_sw = 3.0 / 16.0, w_s = 5.0 / 16.0, w_se = 1.0 / 16.0, damp = 0.8;
-    const uchar4 *row = im.rgba + y * W;
-    uint8_t *out = (to_image ? im.map : maps + (size_t)e * NPIX) + y * W;
-    const uint8_t *tp = im.tile_pal + (y >> 3) * 32;
+    uint8_t *outb = to_image ? im.map : maps + (size_t)e * NPIX;
+    const int up = (i + DITHER_THREADS - 1) & (DITHER_THREADS - 1);  // the thread that owns the row above
     double ea_[3] = {0.0, 0.0, 0.0}, eb[3] = {0.0, 0.0, 0.0}, ec[3] = {0.0, 0.0, 0.0};  // row above: x-1, x, x+1
-    double ee[3] = {0.0, 0.0, 0.0};                                                      // this row: x-1
+    double ee[3] = {0.0, 0.0, 0.0};                                                      // this row: x-1 (all damped)
     uint32_t packed = 0;
+    // four source pixels at a time, requested four steps before their first use
+    uint4 nextq = __ldg(reinterpret_cast<const uint4 *>(im.rgba + i * W));
+    uint4 curq = nextq;
 
     for (int t = 0; t < W + 2 * (H - 1); t++) {
-        const int x = t - 2 * y;
-        if (x >= -1 && x < W) {
+        const int tau = t - 2 * i;
+        if (tau >= -1 && tau < 2 * W) {
+            // the row above published its pixel x+1 in the previous step (for x = 255 this is already pixel 0 of the row
+            // above the thread's second row; the x+1 term of pixel 255 is guarded out below)
+            const bool has_up = i > 0 || tau >= W - 1;
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 ea_[c] = eb[c];
                 eb[c] = ec[c];
-                ec[c] = (y > 0 && x + 1 < W) ? mail[(t - 1) & 1][y - 1][c] : 0.0;
+                ec[c] = has_up ? mail[(t - 1) & 1][up][c] : 0.0;
             }
         }
-        if (x >= 0 && x < W) {
-            const uchar4 p = __ldg(row + x);
-            const int sub = tp[x >> 3] * S;
+        if (tau >= 0 && tau < 2 * W) {
+            const int x = tau & (W - 1), y = i + (tau >> 8) * DITHER_THREADS;
+            if ((x & 3) == 0) {
+                curq = nextq;
+                const int tn = tau + 4;
+                if (tn < 2 * W) nextq = __ldg(reinterpret_cast<const uint4 *>(im.rgba + (i + (tn >> 8) * DITHER_THREADS) * W + (tn & (W - 1))));
+            }
+            const uint32_t pw = (x & 3) == 0 ? curq.x : (x & 3) == 1 ? curq.y : (x & 3) == 2 ? curq.z : curq.w;
+            const int sub = s_tp[(y >> 3) * 32 + (x >> 3)];
             double err[3], target[3];
-            const int o[3] = {p.x, p.y, p.z};
+            const int o[3] = {(int)(pw & 255u), (int)((pw >> 8) & 255u), (int)((pw >> 16) & 255u)};
+            const bool opaque = (pw >> 24) != 0;
             int t8[3];
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 double acc = 0.0;
+                // every stored error is already damped (e * 0.8, the first product of each term of lib.rs:479-493)
                 if (y > 0) {
-                    if (x > 0) acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(ea_[c], damp), w_se));
-                    acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(eb[c], damp), w_s));
-                    if (x + 1 < W) acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(ec[c], damp), w_sw));
+                    if (x > 0) acc = __dadd_rn(acc, __dmul_rn(ea_[c], w_se));
+                    acc = __dadd_rn(acc, __dmul_rn(eb[c], w_s));
+                    if (x + 1 < W) acc = __dadd_rn(acc, __dmul_rn(ec[c], w_sw));
                 }
-                if (x > 0) acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(ee[c], damp), w_e));
+                if (x > 0) acc = __dadd_rn(acc, __dmul_rn(ee[c], w_e));
                 err[c] = acc;
                 target[c] = __dadd_rn((double)o[c], acc);
                 // lib.rs:773-778: clamp(0,255).round() as u8 (half away from zero)
@@ -89,33 +112,36 @@ __global__ void __launch_bounds__(256) k_assign_dither(const ImgDev *imgs, const
                     }
                 }
             } else {
+                // red-mean key (common.cuh) with q = 1024 + r1 + r2: q*dr^2 + 2048*dg^2 + (2558 - q)*db^2
                 int best = 0x7fffffff;
+#pragma unroll 5
                 for (int j = 0; j < S; j++) {
-                    const uchar4 cc = pal[sub + j];
-                    const int key = redmean_key(cc.x, cc.y, cc.z, t8[0], t8[1], t8[2]);
+                    const int4 cc = pal[sub + j];
+                    const int dr = cc.x - t8[0], dg = cc.y - t8[1], db = cc.z - t8[2], q = cc.w + t8[0];
+                    const int key = q * dr * dr + 2048 * dg * dg + (2558 - q) * db * db;
                     if (key < best) {
                         best = key;
                         bi = j;
                     }
                 }
             }
-            const uchar4 nc = pal[sub + bi];
-            if (p.w > 0) {
-                ee[0] = __dsub_rn(target[0], (double)nc.x);
-                ee[1] = __dsub_rn(target[1], (double)nc.y);
-                ee[2] = __dsub_rn(target[2], (double)nc.z);
+            const int4 nc = pal[sub + bi];
+            if (opaque) {
+                ee[0] = __dmul_rn(__dsub_rn(target[0], (double)nc.x), damp);
+                ee[1] = __dmul_rn(__dsub_rn(target[1], (double)nc.y), damp);
+                ee[2] = __dmul_rn(__dsub_rn(target[2], (double)nc.z), damp);
             } else {
-                ee[0] = err[0];
-                ee[1] = err[1];
-                ee[2] = err[2];
+                ee[0] = __dmul_rn(err[0], damp);
+                ee[1] = __dmul_rn(err[1], damp);
+                ee[2] = __dmul_rn(err[2], damp);
                 bi = 0;
             }
-            mail[t & 1][y][0] = ee[0];
-            mail[t & 1][y][1] = ee[1];
-            mail[t & 1][y][2] = ee[2];
-            packed |= (uint32_t)(gi_fmt ? (p.w > 0 ? sub + bi : GI_BLACK) : bi) << (8 * (x & 3));
+            mail[t & 1][i][0] = ee[0];
+            mail[t & 1][i][1] = ee[1];
+            mail[t & 1][i][2] = ee[2];
+            packed |= (uint32_t)(gi_fmt ? (opaque ? sub + bi : GI_BLACK) : bi) << (8 * (x & 3));
             if ((x & 3) == 3) {
-                *reinterpret_cast<uint32_t *>(out + (x & ~3)) = packed;
+                *reinterpret_cast<uint32_t *>(outb + y * W + (x & ~3)) = packed;
                 packed = 0;
             }
         }

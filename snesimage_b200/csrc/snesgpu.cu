@@ -568,9 +568,9 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
         const int gi = (ctx->fused && pl.do_score && !pl.self && !pl.d_maps_out && CS <= 255) ? 1 : 0;
         if (pl.do_assign) {
             if (cfg.dither && cfg.perceptual_palettes) {
-                LAUNCH(ctx, "k_assign_dither<true>", k_assign_dither<true><<<ec, 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self, gi));
+                LAUNCH(ctx, "k_assign_dither<true>", k_assign_dither<true><<<ec, DITHER_THREADS, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self, gi));
             } else if (cfg.dither) {
-                LAUNCH(ctx, "k_assign_dither<false>", k_assign_dither<false><<<ec, 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self, gi));
+                LAUNCH(ctx, "k_assign_dither<false>", k_assign_dither<false><<<ec, DITHER_THREADS, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self, gi));
             } else if (cfg.perceptual_palettes) {
                 LAUNCH(ctx, "k_assign_lab", k_assign_lab<<<dim3(64, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self, gi));
             } else {
