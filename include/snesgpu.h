@@ -75,8 +75,9 @@ int snes_ctx_synchronize(snes_ctx *ctx);
 int snes_ctx_profile_begin(snes_ctx *ctx);
 int snes_ctx_profile_end(snes_ctx *ctx, char *buf, size_t cap, size_t *len);
 /* kernel selection (all variants give the same results; kept switchable for A/B checks):
- *   fused != 0        k_score_fused, blur planes stay in shared memory (default); 0 = multi-kernel pipeline via HBM
- *   block_width       column block of the fused scorer, 16 or 32
+ *   fused             3 = k_score_v3 (default: persistent 4-warp CTAs, packed-f32 horizontal pass), 2 = k_score_v2,
+ *                     1 = k_score_fused (all three keep the blur planes in shared memory); 0 = multi-kernel pipeline via HBM
+ *   block_width       column block of k_score_fused, 16 or 32
  *   delta_assign != 0 without dithering, a candidate re-decides only the pixels its entry can change (default)
  * Env overrides at context creation: SNESGPU_FUSED, SNESGPU_BW, SNESGPU_DELTA. */
 int snes_ctx_set_scorer(snes_ctx *ctx, int fused, int block_width, int delta_assign);
@@ -132,6 +133,13 @@ int snes_batch_eval_candidates(snes_ctx *ctx, snes_image *const *images, int nim
 int snes_batch_eval_candidates_dev(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
                                    const uint8_t *d_cand, int ncand, int cand_idx_base, double *d_scores,
                                    snes_best *d_best);
+/* The first two statements of optimize_palette_entry_{random,channel} in one pass: `best_error = self.error()`
+ * (lib.rs:199, 294; refreshes every image's cached error, which snes_batch_apply_best_dev compares against) followed
+ * by the candidate loop above.  The 3*nimg (image, channel) scoring items of error() share the candidates' scorer
+ * launch instead of running as a launch of their own. */
+int snes_batch_error_eval_candidates_dev(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
+                                         const uint8_t *d_cand, int ncand, int cand_idx_base, double *d_scores,
+                                         snes_best *d_best);
 /* Accept rule of lib.rs:199,216-219,236-237 applied per image after the (possibly cross-rank) argmin:
  * if best[j].err < current error of image j, entry (palette,index) becomes cand_all[j][best[j].idx] and
  * the image is re-optimised; the image's cached error is updated.  d_cand_all holds ncand_all candidates

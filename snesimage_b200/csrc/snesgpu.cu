@@ -61,6 +61,8 @@ struct snes_ctx {
     int nsm = 148;
     int *v3_counter = nullptr;
     float *v3_scratch = nullptr;
+    float *self_xyb = nullptr;        // [img_cap][EVAL_XYB_FLOATS] coarse pyramid of the images' own state (fused error + candidates)
+    double *self_partials = nullptr;  // [img_cap][NSCALES*3*NSUMS]
     int bw = 32;      // column-block width of the fused scorer (16 or 32, SNESGPU_BW)
     int delta = 1;    // 1: no-dither candidates re-decide only the pixels the replaced entry can change (SNESGPU_DELTA)
 
@@ -301,6 +303,8 @@ static void free_scratch(snes_ctx *ctx) {
     cudaFree(ctx->d_km);
     cudaFree(ctx->best);
     cudaFree(ctx->self_scores);
+    cudaFree(ctx->self_xyb);
+    cudaFree(ctx->self_partials);
 }
 
 extern "C" void snes_ctx_destroy(snes_ctx *ctx) {
@@ -449,6 +453,10 @@ static int ensure_imgs(snes_ctx *ctx, size_t n) {
     cudaFree(ctx->d_km);
     cudaFree(ctx->best);
     cudaFree(ctx->self_scores);
+    cudaFree(ctx->self_xyb);
+    cudaFree(ctx->self_partials);
+    ctx->self_xyb = nullptr;
+    ctx->self_partials = nullptr;
     ctx->d_imgs = nullptr;
     ctx->d_km = nullptr;
     ctx->best = nullptr;
@@ -459,6 +467,8 @@ static int ensure_imgs(snes_ctx *ctx, size_t n) {
     RET(dev_alloc(&ctx->d_km, n));
     RET(dev_alloc(&ctx->best, n));
     RET(dev_alloc(&ctx->self_scores, n));
+    RET(dev_alloc(&ctx->self_xyb, n * EVAL_XYB_FLOATS));
+    RET(dev_alloc(&ctx->self_partials, n * NSCALES * 3 * NSUMS));
     ctx->img_cap = n;
     return SNES_OK;
 }
@@ -496,17 +506,22 @@ struct EvalPlan {
     bool do_score = false;            // error()
     uint8_t *d_maps_out = nullptr;    // optional [E][NPIX] device: keep every palette_map
     double *d_scores = nullptr;       // [E] device output of do_score
+    bool with_self_error = false;     // also error() of every image's own state -> ctx->self_scores and the image's cached
+                                      // error, scored inside the first chunk's launch (k_score_v3 only; lib.rs:199, 294)
 };
 
-static int launch_scorer(snes_ctx *ctx, const FusedArgs &fa, int ec) {
+static int launch_scorer(snes_ctx *ctx, const FusedArgs &fa, int ec, const FusedArgs *extra = nullptr, int extra_evals = 0) {
     cudaStream_t st = ctx->stream;
     if (ctx->fused == 3) {
         V3Args va;
         va.f = fa;
         va.nitems = 3 * ec;
+        va.f2 = extra ? *extra : fa;
+        va.nitems2 = extra ? 3 * extra_evals : 0;
         va.counter = ctx->v3_counter;
         va.hscratch = ctx->v3_scratch;
-        const int grid = va.nitems < ctx->nsm * V3_CTAS_PER_SM ? va.nitems : ctx->nsm * V3_CTAS_PER_SM;
+        const int items = va.nitems + va.nitems2;
+        const int grid = items < ctx->nsm * V3_CTAS_PER_SM ? items : ctx->nsm * V3_CTAS_PER_SM;
         CK(cudaMemsetAsync(ctx->v3_counter, 0, sizeof(int), st));
         LAUNCH(ctx, "k_score_v3", k_score_v3<<<grid, V3_THREADS, sizeof(V3Smem), st>>>(va));
     } else if (ctx->fused == 2)
@@ -529,6 +544,27 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
 
     LAUNCH(ctx, "k_tables", k_tables<<<pl.nimg + (pl.ovr >= 0 ? (E + 255) / 256 : 0), 256, 0, st>>>(ctx->d_imgs, pl.nimg, CS, pl.d_cand,
                                                                           pl.ovr >= 0 ? E : 0, ctx->cents, labtab));
+
+    // error() of the images' own state riding in the candidates' scorer launch: its coarse pyramid and partial sums
+    // live in their own buffers; the 3 * nimg extra items join the first chunk
+    const bool self_too = pl.with_self_error && ctx->fused == 3 && pl.do_score && !pl.self;
+    FusedArgs fself;
+    if (self_too) {
+        LAUNCH(ctx, "k_pyramid<false>", k_pyramid<false><<<dim3(16, pl.nimg), 256, 0, st>>>(ctx->d_imgs, ctx->cents, 1, 0, S, CS, -1, nullptr, 1,
+                                                       ctx->self_xyb, nullptr, 1, 0));
+        fself.imgs = ctx->d_imgs;
+        fself.cents = ctx->cents;
+        fself.ncand = 1;
+        fself.e0 = 0;
+        fself.S = S;
+        fself.CS = CS;
+        fself.ovr = -1;
+        fself.maps = nullptr;
+        fself.from_image = 1;
+        fself.gi_fmt = 0;
+        fself.xyb_rm = ctx->self_xyb;
+        fself.partials = ctx->self_partials;
+    }
 
     // no dithering + fused scorer: per-candidate work shrinks to one distance per affected pixel (assign_delta.cuh)
     const bool delta = ctx->fused && ctx->delta && !cfg.dither && pl.do_assign && pl.do_score && !pl.self && !pl.d_maps_out &&
@@ -561,7 +597,7 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
             fa.gi_fmt = 1;
             fa.xyb_rm = ctx->xyb_rm;
             fa.partials = ctx->partials;
-            RET(launch_scorer(ctx, fa, ec));
+            RET(launch_scorer(ctx, fa, ec, (self_too && e0 == 0) ? &fself : nullptr, pl.nimg));
             continue;
         }
         // scratch maps feed only the fused scorer: write global entry indices (no tile_palettes / alpha lookups later)
@@ -597,7 +633,7 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
             fa.gi_fmt = gi;
             fa.xyb_rm = ctx->xyb_rm;
             fa.partials = ctx->partials;
-            RET(launch_scorer(ctx, fa, ec));
+            RET(launch_scorer(ctx, fa, ec, (self_too && e0 == 0) ? &fself : nullptr, pl.nimg));
             continue;
         }
         LAUNCH(ctx, "k_pyramid<false>", k_pyramid<false><<<dim3(16, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self,
@@ -608,6 +644,10 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
             LAUNCH(ctx, "k_blur_v<0>", k_blur_v<0><<<(lines + 127) / 128, 128, 0, st>>>(s, lines, ctx->d_imgs, pl.ncand, e0, ctx->xyb_rm, ctx->hbuf,
                                                            ctx->partials));
         }
+    }
+    if (self_too) {
+        LAUNCH(ctx, "k_pool_fused", k_pool_fused<<<(pl.nimg + 127) / 128, 128, 0, st>>>(ctx->self_partials, pl.nimg, ctx->self_scores));
+        LAUNCH(ctx, "k_store_cur_err", k_store_cur_err<<<(pl.nimg + 127) / 128, 128, 0, st>>>(ctx->d_imgs, pl.nimg, ctx->self_scores));
     }
     if (pl.do_score && ctx->fused) {
         LAUNCH(ctx, "k_pool_fused", k_pool_fused<<<(E + 127) / 128, 128, 0, st>>>(ctx->partials, E, pl.d_scores));
@@ -998,14 +1038,14 @@ static int check_slot(const snes_config &cfg, int palette, int index) {
     return SNES_OK;
 }
 
-extern "C" int snes_batch_eval_candidates_dev(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
-                                              const uint8_t *d_cand, int ncand, int cand_idx_base, double *d_scores,
-                                              snes_best *d_best) {
+static int eval_candidates_dev(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index, const uint8_t *d_cand,
+                               int ncand, int cand_idx_base, double *d_scores, snes_best *d_best, bool with_error) {
     RET(bind_images(ctx, images, nimg));
     const snes_config cfg = images[0]->cfg;
     RET(check_slot(cfg, palette, index));
     if (!d_cand || ncand < 1) return fail(SNES_E_INVALID, "snes_batch_eval_candidates_dev: no candidates");
     RET(ensure_evals(ctx, (size_t)nimg * ncand));
+    if (with_error && ctx->fused != 3) RET(batch_error(ctx, images, nimg));
     EvalPlan pl;
     pl.nimg = nimg;
     pl.ncand = ncand;
@@ -1013,11 +1053,24 @@ extern "C" int snes_batch_eval_candidates_dev(snes_ctx *ctx, snes_image *const *
     pl.d_cand = d_cand;
     pl.do_assign = pl.do_score = true;
     pl.d_scores = d_scores ? d_scores : ctx->scores;
+    pl.with_self_error = with_error && ctx->fused == 3;
     RET(run_plan(ctx, cfg, pl));
     if (d_best) {
         LAUNCH(ctx, "k_argmin", k_argmin<<<nimg, 128, 0, ctx->stream>>>(pl.d_scores, ncand, cand_idx_base, reinterpret_cast<Best *>(d_best)));
     }
     return SNES_OK;
+}
+
+extern "C" int snes_batch_eval_candidates_dev(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
+                                              const uint8_t *d_cand, int ncand, int cand_idx_base, double *d_scores,
+                                              snes_best *d_best) {
+    return eval_candidates_dev(ctx, images, nimg, palette, index, d_cand, ncand, cand_idx_base, d_scores, d_best, false);
+}
+
+extern "C" int snes_batch_error_eval_candidates_dev(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
+                                                    const uint8_t *d_cand, int ncand, int cand_idx_base, double *d_scores,
+                                                    snes_best *d_best) {
+    return eval_candidates_dev(ctx, images, nimg, palette, index, d_cand, ncand, cand_idx_base, d_scores, d_best, true);
 }
 
 extern "C" int snes_batch_eval_candidates(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
@@ -1102,7 +1155,8 @@ static int batch_step(snes_ctx *ctx, snes_image *const *images, int nimg, int pa
     } else {
         LAUNCH(ctx, "k_make_cands", k_make_cands<<<nimg, 64, 0, st>>>(ctx->d_imgs, slot, mode == 1 ? -1 : channel, ctx->cand, ncand));
     }
-    if (mode != 1) RET(batch_error(ctx, images, nimg));  // best_error = self.error() (lib.rs:199, 294)
+    // best_error = self.error() (lib.rs:199, 294): inside the candidates' scorer launch with k_score_v3, else on its own
+    if (mode != 1 && ctx->fused != 3) RET(batch_error(ctx, images, nimg));
     EvalPlan pl;
     pl.nimg = nimg;
     pl.ncand = ncand;
@@ -1110,6 +1164,7 @@ static int batch_step(snes_ctx *ctx, snes_image *const *images, int nimg, int pa
     pl.d_cand = ctx->cand;
     pl.do_assign = pl.do_score = true;
     pl.d_scores = ctx->scores;
+    pl.with_self_error = mode != 1 && ctx->fused == 3;
     RET(run_plan(ctx, cfg, pl));
     LAUNCH(ctx, "k_argmin", k_argmin<<<nimg, 128, 0, st>>>(ctx->scores, ncand, 0, ctx->best));
     LAUNCH(ctx, "k_apply_best", k_apply_best<<<(nimg + 127) / 128, 128, 0, st>>>(ctx->d_imgs, nimg, slot, ctx->cand, ncand, ctx->best, mode == 1));

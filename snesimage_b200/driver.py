@@ -105,13 +105,13 @@ class BatchOptimizer:
         nimg = len(self.images)
         p, i = self.cursor.palette, self.cursor.palette_index
         lo, hi = shard_bounds(ncand_total, self.rank, self.world)
-        engine.batch_error_dev(self.images)                                   # best_error = self.error()  (lib.rs:199)
+        # best_error = self.error() (lib.rs:199) + the candidate loop (lib.rs:205-220) in one pass
         if self.world == 1:
-            engine.batch_eval_candidates_dev(self.images, p, i, d_cand_all.data_ptr(), ncand_total, 0, None, self._best.data_ptr())
+            engine.batch_error_eval_candidates_dev(self.images, p, i, d_cand_all.data_ptr(), ncand_total, 0, None, self._best.data_ptr())
         else:
             # this rank's slice, made contiguous per image
             d_slice = d_cand_all[:, lo:hi, :].contiguous()
-            engine.batch_eval_candidates_dev(self.images, p, i, d_slice.data_ptr(), hi - lo, lo, None, self._best_local.data_ptr())
+            engine.batch_error_eval_candidates_dev(self.images, p, i, d_slice.data_ptr(), hi - lo, lo, None, self._best_local.data_ptr())
             torch.distributed.all_gather_into_tensor(self._best_all, self._best_local, group=self.group)
             engine.merge_best_dev(self.ctx, self._best_all.data_ptr(), self.world, nimg, self._best.data_ptr())
         # accept if strictly better, then optimize() with the winner (lib.rs:216-219, 236-237)

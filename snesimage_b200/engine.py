@@ -108,6 +108,7 @@ _SIGNATURES = {
     "snes_batch_error_dev": (_i, [_vp, _vp, _i, _vp]),
     "snes_batch_eval_candidates": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "snes_batch_eval_candidates_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
+    "snes_batch_error_eval_candidates_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "snes_batch_apply_best_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "snes_merge_best_dev": (_i, [_vp, _vp, _i, _i, _vp]),
     "snes_batch_step_random": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),
@@ -449,6 +450,15 @@ def batch_eval_candidates_dev(images: Sequence[OptimizedImage], palette: int, in
     ctx = _ctx_of(images)
     _check(ctx._l.snes_batch_eval_candidates_dev(ctx._h, _handles(images), len(images), palette, index, d_cand, ncand,
                                                  cand_idx_base, d_scores, d_best), "snes_batch_eval_candidates_dev")
+
+
+def batch_error_eval_candidates_dev(images: Sequence[OptimizedImage], palette: int, index: int, d_cand: int, ncand: int,
+                                    cand_idx_base: int = 0, d_scores: Optional[int] = None, d_best: Optional[int] = None):
+    """`best_error = self.error()` (lib.rs:199, 294) and the candidate loop in one pass: the images' own scoring items
+    share the candidates' scorer launch."""
+    ctx = _ctx_of(images)
+    _check(ctx._l.snes_batch_error_eval_candidates_dev(ctx._h, _handles(images), len(images), palette, index, d_cand, ncand,
+                                                       cand_idx_base, d_scores, d_best), "snes_batch_error_eval_candidates_dev")
 
 
 def batch_apply_best_dev(images: Sequence[OptimizedImage], palette: int, index: int, d_cand_all: int, ncand_all: int, d_best: int):

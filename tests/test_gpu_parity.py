@@ -384,3 +384,56 @@ def test_sharded_argmin_matches_single_rank(ctx):
         assert np.array_equal(a.palette_map, b.palette_map)
     for im in imgs + twins:
         im.close()
+
+
+def test_fused_error_and_candidates_matches_separate_calls(ctx):
+    """snes_batch_error_eval_candidates_dev (error() items riding in the candidates' scorer launch) must give what
+    snes_batch_error_dev followed by snes_batch_eval_candidates_dev gives, bit for bit, and leave the same cached errors."""
+    import torch
+    C, S, nimg, ncand = 4, 7, 3, 10
+    cfg = engine.Config(subpalette_count=C, subpalette_size=S)
+    imgs = [engine.OptimizedImage(ctx, synth.image(120 + j, "T" if j == 1 else "V"), cfg) for j in range(nimg)]
+    engine.batch_initialize_tiles(imgs)
+    engine.batch_recalculate_palettes(imgs)
+    cand = np.stack([synth.candidates(120 + j, 0, ncand) for j in range(nimg)])
+    dev = torch.device("cuda", 0)
+    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream or 1)
+    try:
+        d_cand = torch.from_numpy(cand).to(dev)
+        out = {}
+        for name in ("separate", "fused"):
+            scores = torch.zeros(nimg * ncand, dtype=torch.float64, device=dev)
+            best = torch.zeros(nimg * 2, dtype=torch.int64, device=dev)
+            errs = torch.zeros(nimg, dtype=torch.float64, device=dev)
+            if name == "separate":
+                engine.batch_error_dev(imgs)
+                engine.batch_eval_candidates_dev(imgs, 2, 3, d_cand.data_ptr(), ncand, 0, scores.data_ptr(), best.data_ptr())
+            else:
+                engine.batch_error_eval_candidates_dev(imgs, 2, 3, d_cand.data_ptr(), ncand, 0, scores.data_ptr(), best.data_ptr())
+            engine.batch_apply_best_dev(imgs, 2, 3, d_cand.data_ptr(), ncand, best.data_ptr())
+            torch.cuda.synchronize()
+            out[name] = (scores.cpu().numpy(), best.cpu().numpy().view(engine.BEST_DTYPE), [im.palette.copy() for im in imgs])
+            if name == "separate":   # rewind: same starting state for the fused pass
+                for im in imgs:
+                    im.close()
+                imgs = [engine.OptimizedImage(ctx, synth.image(120 + j, "T" if j == 1 else "V"), cfg) for j in range(nimg)]
+                engine.batch_initialize_tiles(imgs)
+                engine.batch_recalculate_palettes(imgs)
+    finally:
+        ctx.set_stream(None)
+    assert np.array_equal(out["separate"][0], out["fused"][0])
+    assert np.array_equal(out["separate"][1]["idx"], out["fused"][1]["idx"])
+    assert np.array_equal(out["separate"][1]["err"], out["fused"][1]["err"])
+    for a, b in zip(out["separate"][2], out["fused"][2]):
+        assert np.array_equal(a, b)
+    errs_now = [im.error() for im in imgs]
+    o_errs = []
+    for j, im in enumerate(imgs):
+        o = ob.OracleImage(synth.image(120 + j, "T" if j == 1 else "V"), C, S)
+        o.tile_palettes = im.tile_palettes
+        o.palette = im.palette
+        o.optimize()
+        o_errs.append(o.error())
+    assert np.max(np.abs(np.array(errs_now) - np.array(o_errs))) <= TIGHT_TOL
+    for im in imgs:
+        im.close()
