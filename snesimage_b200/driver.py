@@ -150,6 +150,17 @@ class HeadlessRunner:
         self.image.initialize_tiles()        # lib.rs:851
         self.image.recalculate_palettes()    # green button, lib.rs:987-989
 
+    def resume(self, doc):
+        """Continue from a JSON document written by `write_json` / the reference (lib.rs:579-625) instead of running the
+        two k-means initialisations: palette and tile assignment are taken from the document, the per-pixel indices
+        are re-derived by optimize() exactly as the reference does after every change (TODO.md:38-39)."""
+        from . import ingest
+        palette, tile_palettes, _palette_map, _transparent = ingest.state_from_json(doc, self.config.subpalette_count,
+                                                                                     self.config.subpalette_size)
+        self.image.tile_palettes = tile_palettes
+        self.image.palette = palette
+        self.image.optimize()
+
     def iterate(self, n: int = 1):
         im, c = self.image, self.cursor
         for _ in range(n):
