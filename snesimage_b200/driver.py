@@ -137,6 +137,10 @@ class HeadlessRunner:
     """`run()` of the reference without the window: initialize_tiles -> recalculate_palettes -> N
     iterations of the optimiser schedule -> JSON (lib.rs:851-853, 987-989, 889-933, 999-1003)."""
 
+    # Phase of run() (lib.rs:825-830): the green button (lib.rs:982-997) moves TileAssignment -> Clustering (which runs
+    # recalculate_palettes) -> Optimization; the optimiser only iterates in the last phase (lib.rs:889).
+    TILE_ASSIGNMENT, CLUSTERING, OPTIMIZATION = "TileAssignment", "Clustering", "Optimization"
+
     def __init__(self, ctx: engine.Context, rgba: np.ndarray, config: engine.Config, seed: int = 0, ncand: int = 64):
         self.image = engine.OptimizedImage(ctx, rgba, config)
         self.config = config
@@ -145,10 +149,37 @@ class HeadlessRunner:
         self.iteration = 0
         self.last_error = float("inf")
         self.log: List[float] = []
+        self.phase = self.TILE_ASSIGNMENT
+
+    def initialize_tiles(self):
+        self.image.initialize_tiles()        # lib.rs:851
+        self.phase = self.TILE_ASSIGNMENT
+
+    def green_button(self):
+        """lib.rs:982-997"""
+        if self.phase == self.TILE_ASSIGNMENT:
+            self.phase = self.CLUSTERING
+            self.image.recalculate_palettes()
+        elif self.phase == self.CLUSTERING:
+            self.phase = self.OPTIMIZATION
+
+    def click_tile(self, tile_x: int, tile_y: int):
+        """A left click on tile (tile_x, tile_y) of either picture (lib.rs:1005-1024): the tile moves to the next
+        subpalette; outside the TileAssignment phase the palettes are re-clustered at once."""
+        if not (0 <= tile_x < 32 and 0 <= tile_y < 32):
+            raise ValueError("tile out of range")
+        tp = self.image.tile_palettes
+        index = tile_y * 32 + tile_x
+        tp[index] = (int(tp[index]) + 1) % self.config.subpalette_count
+        self.image.tile_palettes = tp
+        if self.phase != self.TILE_ASSIGNMENT:
+            self.image.recalculate_palettes()
 
     def initialize(self):
-        self.image.initialize_tiles()        # lib.rs:851
-        self.image.recalculate_palettes()    # green button, lib.rs:987-989
+        """What a user does before the optimiser runs: start-up, then the green button twice."""
+        self.initialize_tiles()
+        self.green_button()                  # -> Clustering: recalculate_palettes, lib.rs:987-989
+        self.green_button()                  # -> Optimization
 
     def resume(self, doc):
         """Continue from a JSON document written by `write_json` / the reference (lib.rs:579-625) instead of running the
@@ -160,6 +191,7 @@ class HeadlessRunner:
         self.image.tile_palettes = tile_palettes
         self.image.palette = palette
         self.image.optimize()
+        self.phase = self.OPTIMIZATION
 
     def iterate(self, n: int = 1):
         im, c = self.image, self.cursor

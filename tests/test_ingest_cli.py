@@ -147,3 +147,46 @@ def test_headless_trajectory_matches_oracle(ctx, name, kw, n):
     assert r.image.as_json() == o.as_json()
     assert (r.cursor.palette, r.cursor.palette_index, r.cursor.step) == (cur.palette, cur.palette_index, cur.step)
     r.image.close()
+
+
+@pytest.mark.gpu
+def test_phases_and_tile_clicks_match_oracle(ctx):
+    """The interactive part of run() restated headless: tile clicks (lib.rs:1005-1024) before and after the first
+    green button (lib.rs:982-997) give the oracle's state."""
+    from snesimage_b200 import driver, engine
+    rgba = synth.image(44, "B")
+    C, S = 3, 4
+    cfg = engine.Config(subpalette_count=C, subpalette_size=S)
+    r = driver.HeadlessRunner(ctx, rgba, cfg)
+    o = ob.OracleImage(rgba, C, S)
+    r.initialize_tiles()
+    o.initialize_tiles()
+    assert r.phase == r.TILE_ASSIGNMENT
+
+    def o_click(tx, ty, recluster):
+        tp = o.tile_palettes
+        tp[ty * 32 + tx] = (int(tp[ty * 32 + tx]) + 1) % C
+        o.tile_palettes = tp
+        if recluster:
+            o.recalculate_palettes()
+
+    r.click_tile(5, 7)          # TileAssignment: only the assignment changes
+    o_click(5, 7, False)
+    assert np.array_equal(r.image.tile_palettes, o.tile_palettes) and np.array_equal(r.image.palette, o.palette)
+    r.green_button()            # -> Clustering
+    o.recalculate_palettes()
+    assert r.phase == r.CLUSTERING
+    assert np.array_equal(r.image.palette, o.palette) and np.array_equal(r.image.palette_map, o.palette_map)
+    r.click_tile(31, 0)         # later phases: re-cluster at once
+    r.click_tile(31, 0)
+    o_click(31, 0, True)
+    o_click(31, 0, True)
+    assert np.array_equal(r.image.tile_palettes, o.tile_palettes)
+    assert np.array_equal(r.image.palette, o.palette) and np.array_equal(r.image.palette_map, o.palette_map)
+    r.green_button()
+    assert r.phase == r.OPTIMIZATION
+    r.green_button()
+    assert r.phase == r.OPTIMIZATION
+    with pytest.raises(ValueError):
+        r.click_tile(32, 0)
+    r.image.close()
