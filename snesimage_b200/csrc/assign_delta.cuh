@@ -94,10 +94,21 @@ __global__ void __launch_bounds__(256) k_assign_prepare(const ImgDev *imgs, int 
 // and in every mode the row-major XYB planes of scales 1..5 (the fused scorer's inputs): a thread takes
 // 4x4 scale-0 pixels -> 2x2 pixels of scale 1 and one of scale 2; scales 3..5 go through shared memory
 // (downscale_by_2 on linear RGB, then linear_rgb_to_xyb + make_positive_xyb, as ssimulacra2 does).
+//
+// base_xyb (MODE 0 / 1, optional): the coarse pyramids of the images' prepared base assignment, [image][EVAL_XYB_FLOATS].
+// A 4x4 block in which the candidate changes no assignment and no pixel uses the replaced entry has the base image's
+// scale-1 and scale-2 pixels, so they are
+// copied instead of recomputed (three f64-Halley cube roots per pixel); the pixels of the blocks that did change are
+// queued in shared memory and converted by all threads of the CTA afterwards, so that the few changed blocks of a
+// candidate do not serialise whole warps.
+constexpr int PYR_MAXJOBS = 1020;   // a multiple of the 5 pixels a block queues, so a refused block leaves no gap
+
 template <int MODE>
 __global__ void __launch_bounds__(256) k_assign_pyr(const ImgDev *imgs, const CandEntry *cents, int ncand, int e0, int S, int CS,
-                                                    int ovr, uint8_t *maps, float *xyb_rm_base) {
+                                                    int ovr, uint8_t *maps, float *xyb_rm_base, const float *base_xyb) {
     __shared__ float s_lin[MAX_ENTRIES + 1][3];
+    __shared__ float4 s_jobs[(MODE == 2) ? 1 : PYR_MAXJOBS];   // linear RGB + output offset of a queued pixel
+    __shared__ int s_njobs;
     __shared__ float s2[3][32][33];   // linear RGB of the quadrant at scale 2
     __shared__ float s3[3][16][17];
     __shared__ float s4[3][8][9];
@@ -115,6 +126,9 @@ __global__ void __launch_bounds__(256) k_assign_pyr(const ImgDev *imgs, const Ca
     }
     const int psub = (ovr / S) * S, oloc = ovr - psub;
     const int cr = ce.rgb8.x, cg = ce.rgb8.y, cb = ce.rgb8.z;
+    const float *base = (MODE != 2 && base_xyb) ? base_xyb + (size_t)img * EVAL_XYB_FLOATS : nullptr;
+    const uint32_t ovr_rep = (uint32_t)ovr * 0x01010101u;
+    if (tid == 0) s_njobs = 0;
     __syncthreads();
 
     auto store_xyb = [&](int L, int x, int y, const float lin[3]) {
@@ -179,6 +193,7 @@ __global__ void __launch_bounds__(256) k_assign_pyr(const ImgDev *imgs, const Ca
         }
         float l1[2][2][3];
         float quad[4][4][3];
+        bool changed = false;
 #pragma unroll
         for (int r = 0; r < 4; r++) {
             uint32_t out4 = g4[r];
@@ -205,6 +220,10 @@ __global__ void __launch_bounds__(256) k_assign_pyr(const ImgDev *imgs, const Ca
                 }
             }
             if (MODE != 2) *reinterpret_cast<uint32_t *>(map + (y0 + r) * W + x0) = out4;
+            {   // the block differs from the base image if an assignment changed or a pixel sits on the replaced entry
+                const uint32_t v = out4 ^ ovr_rep;
+                changed |= out4 != g4[r] || ((v - 0x01010101u) & ~v & 0x80808080u) != 0;
+            }
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 const int gi = (out4 >> (8 * c)) & 255;
@@ -225,16 +244,54 @@ __global__ void __launch_bounds__(256) k_assign_pyr(const ImgDev *imgs, const Ca
         float l2[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) l2[c] = (((l1[0][0][c] + l1[0][1][c]) + l1[1][0][c]) + l1[1][1][c]) * 0.25f;
+        const size_t o1 = 3 * (size_t)scale_off(1) + (size_t)(y0 >> 1) * 128 + (x0 >> 1);   // scale 1: 128 x 128
+        const size_t o2 = 3 * (size_t)scale_off(2) + (size_t)(y0 >> 2) * 64 + (x0 >> 2);    // scale 2: 64 x 64
+        int slot = -1;
+        if (base && changed) {
+            slot = atomicAdd(&s_njobs, 5);
+            if (slot + 5 > PYR_MAXJOBS) slot = -1;   // queue full: convert in place
+        }
+        if (base && !changed) {
 #pragma unroll
-        for (int a = 0; a < 2; a++)
+            for (int c = 0; c < 3; c++) {
+                const size_t oc = o1 + (size_t)c * 128 * 128;
+                *reinterpret_cast<float2 *>(rm + oc) = __ldg(reinterpret_cast<const float2 *>(base + oc));
+                *reinterpret_cast<float2 *>(rm + oc + 128) = __ldg(reinterpret_cast<const float2 *>(base + oc + 128));
+                rm[o2 + (size_t)c * 64 * 64] = __ldg(base + o2 + (size_t)c * 64 * 64);
+            }
+        } else if (slot >= 0) {
+            s_jobs[slot + 0] = make_float4(l1[0][0][0], l1[0][0][1], l1[0][0][2], __int_as_float((int)o1));
+            s_jobs[slot + 1] = make_float4(l1[0][1][0], l1[0][1][1], l1[0][1][2], __int_as_float((int)o1 + 1));
+            s_jobs[slot + 2] = make_float4(l1[1][0][0], l1[1][0][1], l1[1][0][2], __int_as_float((int)o1 + 128));
+            s_jobs[slot + 3] = make_float4(l1[1][1][0], l1[1][1][1], l1[1][1][2], __int_as_float((int)o1 + 129));
+            s_jobs[slot + 4] = make_float4(l2[0], l2[1], l2[2], __int_as_float(-(int)o2 - 1));   // negative: a scale-2 pixel
+        } else {
 #pragma unroll
-            for (int b = 0; b < 2; b++) store_xyb(1, (x0 >> 1) + b, (y0 >> 1) + a, l1[a][b]);
-        store_xyb(2, x0 >> 2, y0 >> 2, l2);
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int b = 0; b < 2; b++) store_xyb(1, (x0 >> 1) + b, (y0 >> 1) + a, l1[a][b]);
+            store_xyb(2, x0 >> 2, y0 >> 2, l2);
+        }
         s2[0][by][bx] = l2[0];
         s2[1][by][bx] = l2[1];
         s2[2][by][bx] = l2[2];
     }
     __syncthreads();
+    // ---- the queued pixels of the blocks the candidate changed
+    if (MODE != 2) {
+        const int nj = s_njobs < PYR_MAXJOBS ? s_njobs : PYR_MAXJOBS;
+        for (int j = tid; j < nj; j += 256) {
+            const float4 jb = s_jobs[j];
+            const int oi = __float_as_int(jb.w);
+            const size_t o = oi >= 0 ? (size_t)oi : (size_t)(-oi - 1);
+            const size_t plane = oi >= 0 ? (size_t)128 * 128 : (size_t)64 * 64;
+            float xv, yv, bv;
+            lin_to_pxyb(jb.x, jb.y, jb.z, xv, yv, bv);
+            rm[o] = xv;
+            rm[o + plane] = yv;
+            rm[o + 2 * plane] = bv;
+        }
+    }
     // ---- scale 3: 16x16 per quadrant, one pixel per thread ------------------------------------------------------------------
     {
         const int ax = tid & 15, ay = tid >> 4;

@@ -141,7 +141,8 @@ __global__ void __launch_bounds__(256) k_pyramid(const ImgDev *imgs, const CandE
     const ImgDev im = imgs[img];
     float *rm = SRC ? const_cast<float *>(im.xyb_rm) : xyb_rm_base + (size_t)e * EVAL_XYB_FLOATS;
     float *cm = SRC ? const_cast<float *>(im.xyb_cm) : xyb_cm_base + (size_t)e * EVAL_XYB_FLOATS;
-    const uint8_t *map = SRC ? nullptr : (from_image ? im.map : maps + (size_t)e * NPIX);
+    // from_image: 1 = the image's own palette_map, 2 = its prepared base assignment (gi format, assign_delta.cuh)
+    const uint8_t *map = SRC ? nullptr : (from_image == 2 ? im.base_gi : (from_image ? im.map : maps + (size_t)e * NPIX));
     if (!SRC) {
         for (int j = tid; j < CS; j += 256) {
             const bool o = (j == ovr);

@@ -467,7 +467,7 @@ static int ensure_imgs(snes_ctx *ctx, size_t n) {
     RET(dev_alloc(&ctx->d_km, n));
     RET(dev_alloc(&ctx->best, n));
     RET(dev_alloc(&ctx->self_scores, n));
-    RET(dev_alloc(&ctx->self_xyb, n * EVAL_XYB_FLOATS));
+    RET(dev_alloc(&ctx->self_xyb, 2 * n * EVAL_XYB_FLOATS));  // [0, n): own palette_map; [n, 2n): prepared base assignment
     RET(dev_alloc(&ctx->self_partials, n * NSCALES * 3 * NSUMS));
     ctx->img_cap = n;
     return SNES_OK;
@@ -548,8 +548,10 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
     // error() of the images' own state riding in the candidates' scorer launch: its coarse pyramid and partial sums
     // live in their own buffers; the 3 * nimg extra items join the first chunk
     const bool self_too = pl.with_self_error && ctx->fused == 3 && pl.do_score && !pl.self;
+    const bool delta_path = ctx->fused && ctx->delta && !cfg.dither && pl.do_assign && pl.do_score && !pl.self && !pl.d_maps_out &&
+                            pl.ovr >= 0 && CS <= 255;
     FusedArgs fself;
-    if (self_too) {
+    if (self_too) {  // the coarse pyramid of the images' own palette_map: input of their error()
         LAUNCH(ctx, "k_pyramid<false>", k_pyramid<false><<<dim3(16, pl.nimg), 256, 0, st>>>(ctx->d_imgs, ctx->cents, 1, 0, S, CS, -1, nullptr, 1,
                                                        ctx->self_xyb, nullptr, 1, 0));
         fself.imgs = ctx->d_imgs;
@@ -567,13 +569,16 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
     }
 
     // no dithering + fused scorer: per-candidate work shrinks to one distance per affected pixel (assign_delta.cuh)
-    const bool delta = ctx->fused && ctx->delta && !cfg.dither && pl.do_assign && pl.do_score && !pl.self && !pl.d_maps_out &&
-                       pl.ovr >= 0 && CS <= 255;
+    const bool delta = delta_path;
     if (delta) {
         if (cfg.perceptual_palettes)
             LAUNCH(ctx, "k_assign_prepare<true>", k_assign_prepare<true><<<dim3(64, pl.nimg), 256, 0, st>>>(ctx->d_imgs, S, CS, pl.ovr));
         else
             LAUNCH(ctx, "k_assign_prepare<false>", k_assign_prepare<false><<<dim3(64, pl.nimg), 256, 0, st>>>(ctx->d_imgs, S, CS, pl.ovr));
+        // coarse pyramid of the prepared base assignment (current palette, no candidate): k_assign_pyr copies the blocks
+        // a candidate leaves unchanged from it
+        LAUNCH(ctx, "k_pyramid<false>", k_pyramid<false><<<dim3(16, pl.nimg), 256, 0, st>>>(ctx->d_imgs, ctx->cents, 1, 0, S, CS, -1, nullptr, 2,
+                                                       ctx->self_xyb + (size_t)ctx->img_cap * EVAL_XYB_FLOATS, nullptr, 1, 1));
     }
 
     for (int e0 = 0; e0 < E; e0 += chunk) {
@@ -581,9 +586,9 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
         uint8_t *maps = pl.d_maps_out ? pl.d_maps_out + (size_t)e0 * NPIX : ctx->maps;
         if (delta) {
             if (cfg.perceptual_palettes)
-                LAUNCH(ctx, "k_assign_pyr<1>", k_assign_pyr<1><<<dim3(4, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, ctx->xyb_rm));
+                LAUNCH(ctx, "k_assign_pyr<1>", k_assign_pyr<1><<<dim3(4, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, ctx->xyb_rm, ctx->self_xyb + (size_t)ctx->img_cap * EVAL_XYB_FLOATS));
             else
-                LAUNCH(ctx, "k_assign_pyr<0>", k_assign_pyr<0><<<dim3(4, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, ctx->xyb_rm));
+                LAUNCH(ctx, "k_assign_pyr<0>", k_assign_pyr<0><<<dim3(4, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, ctx->xyb_rm, ctx->self_xyb + (size_t)ctx->img_cap * EVAL_XYB_FLOATS));
             FusedArgs fa;
             fa.imgs = ctx->d_imgs;
             fa.cents = ctx->cents;
@@ -616,7 +621,7 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
         if (!pl.do_score) continue;
         if (ctx->fused) {
             if (gi)
-                LAUNCH(ctx, "k_assign_pyr<2>", k_assign_pyr<2><<<dim3(4, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, ctx->xyb_rm));
+                LAUNCH(ctx, "k_assign_pyr<2>", k_assign_pyr<2><<<dim3(4, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, ctx->xyb_rm, nullptr));
             else
                 LAUNCH(ctx, "k_pyramid<false>", k_pyramid<false><<<dim3(16, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self,
                                                        ctx->xyb_rm, ctx->xyb_cm, 1, gi));

@@ -437,3 +437,42 @@ def test_fused_error_and_candidates_matches_separate_calls(ctx):
     assert np.max(np.abs(np.array(errs_now) - np.array(o_errs))) <= TIGHT_TOL
     for im in imgs:
         im.close()
+
+
+@pytest.mark.parametrize("lab", [False, True])
+def test_eval_candidates_near_current_entry(ctx, lab):
+    """Candidates one step away from the current colour: most pixels of the entry keep their assignment while the entry's
+    colour changes, and most 4x4 blocks of the image are untouched -- the case the delta assignment and the copied
+    pyramid blocks (assign_delta.cuh) must get right.  The state comes from k-means + optimize, so entries are in use."""
+    rgba = synth.image(57, "V")
+    C, S = 4, 7
+    g, o = make_pair(ctx, rgba, C, S, lab=lab, random_state=False)
+    for im in (g, o):
+        im.initialize_tiles()
+        im.recalculate_palettes()
+    p, i = 2, 3
+    cur = o.palette[p * S + i].astype(np.int64)
+    cand = np.stack([np.clip(cur + d, 0, 31) for d in ([0, 0, 0], [1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1],
+                                                       [0, 0, -1], [1, 1, 1], [-2, 3, -1])]).astype(np.uint8)
+    so = o.eval_candidates(p, i, cand)
+    if lab:
+        sg = g.eval_candidates(p, i, cand)
+        assert np.max(np.abs(sg - so)) <= 1e-4, (sg, so)   # CIELAB choices may differ on a handful of pixels (DESIGN.md)
+    else:
+        sg, mg = g.eval_candidates(p, i, cand, want_maps=True)
+        _, mo = o.eval_candidates(p, i, cand, want_maps=True)
+        assert np.array_equal(mg, mo)
+        assert np.max(np.abs(sg - so)) <= TIGHT_TOL, (sg, so)
+        assert sg[0] == g.error()   # the unchanged colour scores the image's own error, bitwise
+    r = engine.batch_eval_candidates([g], p, i, cand[None])   # scratch-map path (delta assignment + copied blocks)
+    assert np.max(np.abs(r["scores"][0] - so)) <= (1e-4 if lab else TIGHT_TOL)
+    # a palette changed through the setter leaves palette_map stale until the next optimize(); a candidate evaluation
+    # (set entry, optimize(), error(): lib.rs:209-214) must not depend on that stale map
+    pal = o.palette.copy()
+    pal[0 * S + 1] = (pal[0 * S + 1].astype(np.int64) + [3, -2, 1]).clip(0, 31)
+    g.palette = pal
+    o.palette = pal
+    so2 = o.eval_candidates(p, i, cand)
+    r2 = engine.batch_eval_candidates([g], p, i, cand[None])
+    assert np.max(np.abs(r2["scores"][0] - so2)) <= (1e-4 if lab else TIGHT_TOL)
+    g.close()
