@@ -1,0 +1,21 @@
+"""Small end-to-end case for compute-sanitizer (memcheck / racecheck): every kernel of the candidate path once, in all
+four modes, on one image with a handful of candidates."""
+import sys
+
+import numpy as np
+
+sys.path.insert(0, ".")
+from snesimage_b200 import engine, synth
+
+ctx = engine.Context(0)
+for name, kw in {"rgb": {}, "lab": {"perceptual_palettes": True}, "dither": {"dither": True}, "nes": {"nes": True, "dither": True}}.items():
+    cfg = engine.Config(subpalette_count=3, subpalette_size=4, **kw)
+    im = engine.OptimizedImage(ctx, synth.image(5, "T"), cfg)
+    im.initialize_tiles()
+    im.recalculate_palettes()
+    cand = synth.candidates(5, 0, 3)
+    r = engine.batch_eval_candidates([im], 1, 2, cand[None])
+    engine.batch_step_random([im], 1, 2, cand[None])
+    print(name, r["scores"][0], im.error(), flush=True)
+    im.close()
+ctx.close()
