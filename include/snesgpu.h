@@ -160,6 +160,19 @@ int snes_batch_step_nes(snes_ctx *ctx, snes_image *const *images, int nimg, int 
 int snes_batch_step_channel(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index, int channel,
                             snes_best *best, double *errors_after);
 
+/* ---- tile reassignment as evaluated candidates ------------------------------------------------ */
+/* The reference changes a tile's subpalette only by hand (a click cycles it, lib.rs:1005-1017; TODO.md:36-37 wishes for
+ * an automatic version).  Here a move is a candidate like a palette colour: for image j and move k,
+ * tile_palettes[moves[j][k][0]] = moves[j][k][1]; optimize(); error().  moves: nimg*nmoves pairs (tile index =
+ * tile_y*32 + tile_x, subpalette).  scores[nimg*nmoves], maps[nimg*nmoves*65536], best[nimg] optional; the images' own
+ * state is not modified. */
+int snes_batch_eval_tile_moves(snes_ctx *ctx, snes_image *const *images, int nimg, const int32_t *moves, int nmoves,
+                               double *scores, uint8_t *maps, snes_best *best);
+/* Evaluate, then apply each image's best move if it is strictly better than the image's error() (the accept rule of
+ * lib.rs:216-219) and optimize().  applied[nimg] (optional): 1 where a move was taken. */
+int snes_batch_step_tile_moves(snes_ctx *ctx, snes_image *const *images, int nimg, const int32_t *moves, int nmoves,
+                               snes_best *best, uint8_t *applied);
+
 /* ---- colour primitives exposed for tests (lib.rs:628-795, 1080-1100) ------------------------- */
 /* Nearest entry for n targets (f64 triples) against a list of ncolors 5-bit colours on the GPU. */
 int snes_closest_color_index(snes_ctx *ctx, const uint8_t *colors5, int ncolors, const double *targets, int n,

@@ -67,6 +67,12 @@ struct ImgDev {
     int *excl_key;            // [NPIX] its key (int32 red-mean key, or f32 CIEDE2000 bits)
 };
 
+// A tile-reassignment candidate: tile `tile` (tile_y * 32 + tile_x) bound to subpalette `sub` instead of
+// tile_palettes[tile] (what a click on the tile does, lib.rs:1005-1017, as an evaluated candidate; TODO.md:36-37).
+struct TileMove {
+    int32_t tile, sub;
+};
+
 struct Best {
     double err;
     int32_t idx;

@@ -27,7 +27,8 @@ constexpr int DITHER_THREADS = 128;
 // of thread i - 1 (thread 127 for the first pixel of row 128), so the mailbox is indexed by thread.
 template <bool LAB>
 __global__ void __launch_bounds__(DITHER_THREADS) k_assign_dither(const ImgDev *imgs, const CandEntry *cents, int ncand, int e0, int S,
-                                                                  int CS, int ovr, uint8_t *maps, int to_image, int gi_fmt) {
+                                                                  int CS, int ovr, uint8_t *maps, int to_image, int gi_fmt,
+                                                                  const TileMove *moves /* per evaluation, or null */) {
     __shared__ int4 pal[MAX_ENTRIES];  // r, g, b of as_rgba(entry), 1024 + r
     __shared__ float4 pal_lab[LAB ? MAX_ENTRIES : 1];
     __shared__ uint8_t s_tp[NTILES];   // tile_palettes * S
@@ -42,7 +43,8 @@ __global__ void __launch_bounds__(DITHER_THREADS) k_assign_dither(const ImgDev *
             pal_lab[j] = make_float4(l[0], l[1], l[2], 0.0f);
         }
     }
-    for (int j = i; j < NTILES; j += DITHER_THREADS) s_tp[j] = (uint8_t)(im.tile_pal[j] * S);
+    for (int j = i; j < NTILES; j += DITHER_THREADS)
+        s_tp[j] = (uint8_t)(((moves && moves[ea].tile == j) ? moves[ea].sub : im.tile_pal[j]) * S);
     for (int c = 0; c < 3; c++) mail[0][i][c] = mail[1][i][c] = 0.0;
     __syncthreads();
 

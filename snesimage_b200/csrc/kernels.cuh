@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(256) k_tables(const ImgDev *imgs, int nimg, in
 // gi_fmt != 0 (scratch maps of the fused scorer): each byte is the global entry index tile_sub*S + index, or
 // GI_BLACK for a transparent pixel, so the scorer needs neither tile_palettes nor alpha to render the pixel.
 __global__ void __launch_bounds__(256) k_assign_rgb(const ImgDev *imgs, const CandEntry *cents, int ncand, int e0, int S,
-                                                    int CS, int ovr, uint8_t *maps, int to_image, int gi_fmt) {
+                                                    int CS, int ovr, uint8_t *maps, int to_image, int gi_fmt,
+                                                    const TileMove *moves /* per evaluation, or null */) {
     __shared__ uchar4 pal[MAX_ENTRIES];
     const int e = blockIdx.y, ea = e0 + e, img = ea / ncand, tid = threadIdx.x;
     const ImgDev im = imgs[img];
@@ -96,7 +97,8 @@ __global__ void __launch_bounds__(256) k_assign_rgb(const ImgDev *imgs, const Ca
     const int q = blockIdx.x * 256 + tid;  // quad-of-4 index
     const int px0 = q * 4, y = px0 >> 8, x = px0 & 255;
     const uint4 v = __ldg(reinterpret_cast<const uint4 *>(im.rgba) + q);
-    const int sub = im.tile_pal[(y >> 3) * 32 + (x >> 3)] * S;
+    const int tile = (y >> 3) * 32 + (x >> 3);
+    const int sub = ((moves && moves[ea].tile == tile) ? moves[ea].sub : im.tile_pal[tile]) * S;
     const uint32_t pix[4] = {v.x, v.y, v.z, v.w};
     uint32_t packed = 0;
 #pragma unroll
@@ -563,6 +565,25 @@ __global__ void k_apply_best(const ImgDev *imgs, int nimg, int slot, const uint8
         im.palette[3 * slot + 2] = c[2];
         *im.cur_err = b.err;
     }
+}
+
+// k_apply_tile_move: the accept step for tile-reassignment candidates: image j takes its best move if that is strictly
+// better than its current error (the rule of lib.rs:216-219 applied to tile_palettes instead of a palette entry).
+__global__ void k_apply_tile_move(const ImgDev *imgs, int nimg, const TileMove *moves, int nmoves, const Best *best, uint8_t *applied) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nimg) return;
+    const Best b = best[j];
+    uint8_t took = 0;
+    if (b.idx >= 0 && b.idx < nmoves) {
+        const ImgDev im = imgs[j];
+        if (b.err < *im.cur_err) {
+            const TileMove m = moves[(size_t)j * nmoves + b.idx];
+            im.tile_pal[m.tile] = (uint8_t)m.sub;
+            *im.cur_err = b.err;
+            took = 1;
+        }
+    }
+    if (applied) applied[j] = took;
 }
 
 // current error of each image := scores[j]  (after an error() pass over the images themselves)

@@ -157,7 +157,8 @@ __global__ void __launch_bounds__(256) k_image_lab(const uchar4 *rgba, float4 *l
 // k_assign_lab: optimize() (lib.rs:425-501) without dithering, CIEDE2000 metric.  Same launch shape
 // and outputs as k_assign_rgb: grid (64, E), block 256, 4 pixels per thread.
 __global__ void __launch_bounds__(256) k_assign_lab(const ImgDev *imgs, const CandEntry *cents, int ncand, int e0, int S,
-                                                    int CS, int ovr, uint8_t *maps, int to_image, int gi_fmt) {
+                                                    int CS, int ovr, uint8_t *maps, int to_image, int gi_fmt,
+                                                    const TileMove *moves /* per evaluation, or null */) {
     __shared__ float4 pal[MAX_ENTRIES];
     const int e = blockIdx.y, ea = e0 + e, img = ea / ncand, tid = threadIdx.x;
     const ImgDev im = imgs[img];
@@ -168,7 +169,8 @@ __global__ void __launch_bounds__(256) k_assign_lab(const ImgDev *imgs, const Ca
     __syncthreads();
     const int q = blockIdx.x * 256 + tid;
     const int px0 = q * 4, y = px0 >> 8, x = px0 & 255;
-    const int sub = im.tile_pal[(y >> 3) * 32 + (x >> 3)] * S;
+    const int tile = (y >> 3) * 32 + (x >> 3);
+    const int sub = ((moves && moves[ea].tile == tile) ? moves[ea].sub : im.tile_pal[tile]) * S;
     uint32_t packed = 0;
 #pragma unroll 1
     for (int k = 0; k < 4; k++) {

@@ -506,6 +506,7 @@ struct EvalPlan {
     bool do_score = false;            // error()
     uint8_t *d_maps_out = nullptr;    // optional [E][NPIX] device: keep every palette_map
     double *d_scores = nullptr;       // [E] device output of do_score
+    const TileMove *d_moves = nullptr;  // [E] device: tile-reassignment candidates (ovr < 0); null = none
     bool with_self_error = false;     // also error() of every image's own state -> ctx->self_scores and the image's cached
                                       // error, scored inside the first chunk's launch (k_score_v3 only; lib.rs:199, 294)
 };
@@ -609,13 +610,13 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
         const int gi = (ctx->fused && pl.do_score && !pl.self && !pl.d_maps_out && CS <= 255) ? 1 : 0;
         if (pl.do_assign) {
             if (cfg.dither && cfg.perceptual_palettes) {
-                LAUNCH(ctx, "k_assign_dither<true>", k_assign_dither<true><<<ec, DITHER_THREADS, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self, gi));
+                LAUNCH(ctx, "k_assign_dither<true>", k_assign_dither<true><<<ec, DITHER_THREADS, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self, gi, pl.d_moves));
             } else if (cfg.dither) {
-                LAUNCH(ctx, "k_assign_dither<false>", k_assign_dither<false><<<ec, DITHER_THREADS, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self, gi));
+                LAUNCH(ctx, "k_assign_dither<false>", k_assign_dither<false><<<ec, DITHER_THREADS, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self, gi, pl.d_moves));
             } else if (cfg.perceptual_palettes) {
-                LAUNCH(ctx, "k_assign_lab", k_assign_lab<<<dim3(64, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self, gi));
+                LAUNCH(ctx, "k_assign_lab", k_assign_lab<<<dim3(64, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self, gi, pl.d_moves));
             } else {
-                LAUNCH(ctx, "k_assign_rgb", k_assign_rgb<<<dim3(64, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self, gi));
+                LAUNCH(ctx, "k_assign_rgb", k_assign_rgb<<<dim3(64, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self, gi, pl.d_moves));
             }
         }
         if (!pl.do_score) continue;
@@ -1116,6 +1117,90 @@ extern "C" int snes_batch_eval_candidates(snes_ctx *ctx, snes_image *const *imag
     };
     if (rc == SNES_OK) rc = copy_out();
     if (d_maps) cudaFree(d_maps);
+    return rc;
+}
+
+// ---- tile reassignment as evaluated candidates (TODO.md:36-37) ------------------------------
+static int upload_moves(snes_ctx *ctx, const snes_config &cfg, const int32_t *moves, size_t n, TileMove **d_out) {
+    if (!moves || n < 1) return fail(SNES_E_INVALID, "tile moves: no candidates");
+    for (size_t i = 0; i < n; i++)
+        if (moves[2 * i] < 0 || moves[2 * i] >= NTILES || moves[2 * i + 1] < 0 || moves[2 * i + 1] >= cfg.subpalette_count)
+            return fail(SNES_E_INVALID, "tile moves: tile must be in 0..1023 and subpalette below subpalette_count");
+    TileMove *d = nullptr;
+    CK(cudaMalloc((void **)&d, sizeof(TileMove) * n));
+    cudaError_t e = cudaMemcpyAsync(d, moves, sizeof(TileMove) * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        return fail(SNES_E_CUDA, cudaGetErrorString(e));
+    }
+    *d_out = d;
+    return SNES_OK;
+}
+
+static int eval_tile_moves(snes_ctx *ctx, snes_image *const *images, int nimg, const snes_config &cfg, const TileMove *d_moves,
+                           int nmoves, uint8_t *d_maps) {
+    EvalPlan pl;
+    pl.nimg = nimg;
+    pl.ncand = nmoves;
+    pl.ovr = -1;
+    pl.d_moves = d_moves;
+    pl.do_assign = pl.do_score = true;
+    pl.d_maps_out = d_maps;
+    pl.d_scores = ctx->scores;
+    RET(run_plan(ctx, cfg, pl));
+    LAUNCH(ctx, "k_argmin", k_argmin<<<nimg, 128, 0, ctx->stream>>>(ctx->scores, nmoves, 0, ctx->best));
+    return SNES_OK;
+}
+
+extern "C" int snes_batch_eval_tile_moves(snes_ctx *ctx, snes_image *const *images, int nimg, const int32_t *moves, int nmoves,
+                                          double *scores, uint8_t *maps, snes_best *best) {
+    RET(bind_images(ctx, images, nimg));
+    const snes_config cfg = images[0]->cfg;
+    const size_t E = (size_t)nimg * (nmoves > 0 ? nmoves : 0);
+    TileMove *d_moves = nullptr;
+    RET(upload_moves(ctx, cfg, moves, E, &d_moves));
+    uint8_t *d_maps = nullptr;
+    cudaStream_t st = ctx->stream;
+    int rc = [&]() -> int {
+        RET(ensure_evals(ctx, E));
+        if (maps) CK(cudaMalloc((void **)&d_maps, E * NPIX));
+        RET(eval_tile_moves(ctx, images, nimg, cfg, d_moves, nmoves, d_maps));
+        if (scores) CK(cudaMemcpyAsync(scores, ctx->scores, sizeof(double) * E, cudaMemcpyDeviceToHost, st));
+        if (best) CK(cudaMemcpyAsync(best, ctx->best, sizeof(Best) * nimg, cudaMemcpyDeviceToHost, st));
+        if (maps) CK(cudaMemcpyAsync(maps, d_maps, E * NPIX, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return SNES_OK;
+    }();
+    cudaStreamSynchronize(st);
+    cudaFree(d_moves);
+    if (d_maps) cudaFree(d_maps);
+    return rc;
+}
+
+extern "C" int snes_batch_step_tile_moves(snes_ctx *ctx, snes_image *const *images, int nimg, const int32_t *moves, int nmoves,
+                                          snes_best *best, uint8_t *applied) {
+    RET(bind_images(ctx, images, nimg));
+    const snes_config cfg = images[0]->cfg;
+    const size_t E = (size_t)nimg * (nmoves > 0 ? nmoves : 0);
+    TileMove *d_moves = nullptr;
+    RET(upload_moves(ctx, cfg, moves, E, &d_moves));
+    uint8_t *d_applied = nullptr;
+    cudaStream_t st = ctx->stream;
+    int rc = [&]() -> int {
+        RET(ensure_evals(ctx, E));
+        CK(cudaMalloc((void **)&d_applied, nimg));
+        RET(batch_error(ctx, images, nimg));   // the error the best move has to beat
+        RET(eval_tile_moves(ctx, images, nimg, cfg, d_moves, nmoves, nullptr));
+        LAUNCH(ctx, "k_apply_tile_move", k_apply_tile_move<<<(nimg + 127) / 128, 128, 0, st>>>(ctx->d_imgs, nimg, d_moves, nmoves, ctx->best, d_applied));
+        RET(batch_optimize(ctx, images, nimg));
+        if (best) CK(cudaMemcpyAsync(best, ctx->best, sizeof(Best) * nimg, cudaMemcpyDeviceToHost, st));
+        if (applied) CK(cudaMemcpyAsync(applied, d_applied, nimg, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return SNES_OK;
+    }();
+    cudaStreamSynchronize(st);
+    cudaFree(d_moves);
+    if (d_applied) cudaFree(d_applied);
     return rc;
 }
 

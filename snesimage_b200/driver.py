@@ -175,6 +175,20 @@ class HeadlessRunner:
         if self.phase != self.TILE_ASSIGNMENT:
             self.image.recalculate_palettes()
 
+    def optimize_tile(self, tile_x: int, tile_y: int) -> bool:
+        """The automatic version of a tile click (TODO.md:36-37): every other subpalette is tried for the tile
+        (optimize() + error() each, one batch on the GPU) and the best is kept if it is strictly better than the
+        current error.  Returns whether the tile moved."""
+        if not (0 <= tile_x < 32 and 0 <= tile_y < 32):
+            raise ValueError("tile out of range")
+        index = tile_y * 32 + tile_x
+        cur = int(self.image.tile_palettes[index])
+        moves = [(index, q) for q in range(self.config.subpalette_count) if q != cur]
+        if not moves:
+            return False
+        r = engine.batch_step_tile_moves([self.image], np.asarray(moves, np.int32)[None])
+        return bool(r["applied"][0])
+
     def initialize(self):
         """What a user does before the optimiser runs: start-up, then the green button twice."""
         self.initialize_tiles()

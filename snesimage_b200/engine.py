@@ -114,6 +114,8 @@ _SIGNATURES = {
     "snes_batch_step_random": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),
     "snes_batch_step_nes": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "snes_batch_step_channel": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "snes_batch_eval_tile_moves": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
+    "snes_batch_step_tile_moves": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
     "snes_closest_color_index": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp]),
     "snes_new_nes_only": (_i, [_vp, _vp, _i, _i, _vp]),
     "snes_image_debug_planes": (_i, [_vp, _vp, _vp, _vp]),
@@ -440,6 +442,39 @@ def batch_step_channel(images: Sequence[OptimizedImage], palette: int, index: in
 
 
 # ---- device-pointer (asynchronous) entry points, used by bench.py and the multi-GPU driver --------
+def _moves(moves, nimg: int) -> np.ndarray:
+    m = np.ascontiguousarray(np.asarray(moves, dtype=np.int32))
+    return m.reshape(nimg, -1, 2)
+
+
+def batch_eval_tile_moves(images: Sequence[OptimizedImage], moves, want_maps: bool = False) -> dict:
+    """Tile reassignment as evaluated candidates (TODO.md:36-37): for image j and move k = (tile, subpalette),
+    tile_palettes[tile] = subpalette; optimize(); error().  moves: (nimg, nmoves, 2) int32, tile = tile_y*32 + tile_x.
+    The images' own state is not modified."""
+    ctx = _ctx_of(images)
+    nimg = len(images)
+    m = _moves(moves, nimg)
+    nmoves = m.shape[1]
+    scores = np.zeros((nimg, nmoves), np.float64)
+    maps = np.zeros((nimg, nmoves, 256, 256), np.uint8) if want_maps else None
+    best = np.zeros(nimg, BEST_DTYPE)
+    _check(ctx._l.snes_batch_eval_tile_moves(ctx._h, _handles(images), nimg, _ptr(m), nmoves, _ptr(scores), _ptr(maps), _ptr(best)),
+           "snes_batch_eval_tile_moves")
+    return {"scores": scores, "maps": maps, "best": best}
+
+
+def batch_step_tile_moves(images: Sequence[OptimizedImage], moves) -> dict:
+    """Evaluate the moves and apply each image's best one if it is strictly better than the image's error()."""
+    ctx = _ctx_of(images)
+    nimg = len(images)
+    m = _moves(moves, nimg)
+    best = np.zeros(nimg, BEST_DTYPE)
+    applied = np.zeros(nimg, np.uint8)
+    _check(ctx._l.snes_batch_step_tile_moves(ctx._h, _handles(images), nimg, _ptr(m), m.shape[1], _ptr(best), _ptr(applied)),
+           "snes_batch_step_tile_moves")
+    return {"best": best, "applied": applied.astype(bool)}
+
+
 def batch_error_dev(images: Sequence[OptimizedImage], d_errors: Optional[int] = None):
     ctx = _ctx_of(images)
     _check(ctx._l.snes_batch_error_dev(ctx._h, _handles(images), len(images), d_errors), "snes_batch_error_dev")

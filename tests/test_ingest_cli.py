@@ -190,3 +190,62 @@ def test_phases_and_tile_clicks_match_oracle(ctx):
     with pytest.raises(ValueError):
         r.click_tile(32, 0)
     r.image.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", [dict(), dict(dither=True), dict(perceptual_palettes=True)])
+def test_tile_moves_match_oracle(ctx, kw):
+    """Tile reassignment candidates: score of `tile_palettes[t] = q; optimize(); error()` for a batch of
+    moves equals the oracle's, the accept rule takes the strict best, and the runner's optimize_tile applies it."""
+    from snesimage_b200 import driver, engine
+    rgba = synth.image(61, "B")
+    C, S = 3, 4
+    cfg = engine.Config(subpalette_count=C, subpalette_size=S, **kw)
+    lab = bool(kw.get("perceptual_palettes"))
+    r = driver.HeadlessRunner(ctx, rgba, cfg)
+    o = ob.OracleImage(rgba, C, S, cfg.dither, cfg.perceptual_palettes, cfg.nes)
+    r.initialize()
+    o.initialize_tiles()
+    o.recalculate_palettes()
+    tp0 = o.tile_palettes.copy()
+    tiles = [0, 37, 500, 1023]
+    moves = [(t, (int(tp0[t]) + d) % C) for t in tiles for d in (1, 2)]
+    want = []
+    for t, q in moves:
+        tp = tp0.copy()
+        tp[t] = q
+        o.tile_palettes = tp
+        o.optimize()
+        want.append((o.error(), o.palette_map.copy()))
+    o.tile_palettes = tp0
+    o.optimize()
+    got = engine.batch_eval_tile_moves([r.image], np.asarray(moves, np.int32)[None], want_maps=not lab)
+    tol = 1e-4 if lab else 1e-8
+    assert np.max(np.abs(got["scores"][0] - np.array([w[0] for w in want]))) <= tol
+    if not lab:
+        for k, w in enumerate(want):
+            assert np.array_equal(got["maps"][0, k], w[1]), moves[k]
+    assert np.array_equal(r.image.tile_palettes, tp0)              # evaluation leaves the state alone
+    k = int(np.argmin(got["scores"][0]))
+    assert got["best"]["idx"][0] == k
+    # accept: strictly better than the current error, else nothing changes
+    cur = o.error()
+    s = engine.batch_step_tile_moves([r.image], np.asarray(moves, np.int32)[None])
+    take = want[k][0] < cur
+    assert bool(s["applied"][0]) == take
+    tp = tp0.copy()
+    if take:
+        tp[moves[k][0]] = moves[k][1]
+    assert np.array_equal(r.image.tile_palettes, tp)
+    o.tile_palettes = tp
+    o.optimize()
+    if not lab:
+        assert np.array_equal(r.image.palette_map, o.palette_map)
+    assert abs(r.image.error() - o.error()) <= tol
+    # the runner's automatic tile click
+    before = r.image.error()
+    moved = r.optimize_tile(5, 9)
+    assert r.image.error() <= before and (moved == (r.image.error() < before))
+    with pytest.raises(engine.SnesGpuError):
+        engine.batch_eval_tile_moves([r.image], np.asarray([[(2000, 0)]], np.int32))
+    r.image.close()
