@@ -607,7 +607,24 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
             continue;
         }
         // scratch maps feed only the fused scorer: write global entry indices (no tile_palettes / alpha lookups later)
-        const int gi = (ctx->fused && pl.do_score && !pl.self && !pl.d_maps_out && CS <= 255) ? 1 : 0;
+        int gi = (ctx->fused && pl.do_score && !pl.self && !pl.d_maps_out && CS <= 255) ? 1 : 0;
+        if (pl.d_moves && pl.do_score) {
+            // a tile move changes the tile's subpalette for this evaluation only, so the scorer must not look it up in
+            // the image: score from a gi-format scratch map; a palette_map-format copy for the caller is a second pass
+            gi = 1;
+            if (pl.d_maps_out) {
+                uint8_t *outm = maps;
+                if (cfg.dither && cfg.perceptual_palettes)
+                    LAUNCH(ctx, "k_assign_dither<true>", k_assign_dither<true><<<ec, DITHER_THREADS, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, outm, 0, 0, pl.d_moves));
+                else if (cfg.dither)
+                    LAUNCH(ctx, "k_assign_dither<false>", k_assign_dither<false><<<ec, DITHER_THREADS, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, outm, 0, 0, pl.d_moves));
+                else if (cfg.perceptual_palettes)
+                    LAUNCH(ctx, "k_assign_lab", k_assign_lab<<<dim3(64, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, outm, 0, 0, pl.d_moves));
+                else
+                    LAUNCH(ctx, "k_assign_rgb", k_assign_rgb<<<dim3(64, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, outm, 0, 0, pl.d_moves));
+                maps = ctx->maps;
+            }
+        }
         if (pl.do_assign) {
             if (cfg.dither && cfg.perceptual_palettes) {
                 LAUNCH(ctx, "k_assign_dither<true>", k_assign_dither<true><<<ec, DITHER_THREADS, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self, gi, pl.d_moves));
@@ -1139,6 +1156,8 @@ static int upload_moves(snes_ctx *ctx, const snes_config &cfg, const int32_t *mo
 
 static int eval_tile_moves(snes_ctx *ctx, snes_image *const *images, int nimg, const snes_config &cfg, const TileMove *d_moves,
                            int nmoves, uint8_t *d_maps) {
+    if (!ctx->fused || cfg.subpalette_count * cfg.subpalette_size > 255)
+        return fail(SNES_E_INVALID, "tile moves need a fused scorer and subpalette_count * subpalette_size <= 255");
     EvalPlan pl;
     pl.nimg = nimg;
     pl.ncand = nmoves;
