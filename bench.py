@@ -8,7 +8,8 @@ optimize().  Weak scaling: every rank evaluates 64 candidates per image (64*N pe
 exchange is the all-gather argmin of 16 bytes per image.
 
   value     whole-job candidate evaluations / s, candidate lists resident in HBM (device-timed, max over ranks)
-  e2e       the same step driven from pinned host buffers: candidate H2D + winning records D2H every step
+  e2e       the same step through the host-buffer entry point of the C ABI (snes_batch_step_random): candidate H2D +
+            winning records D2H inside every call (N > 1: pinned host buffers around the sharded device-pointer step)
   roofline  the dominant kernel's algorithmic bytes / its CUDA-event time, against MEASURED_PEAKS.json
   cpu_baseline  the CPU oracle (C restatement of the reference) on this box's host cores, bounded sample
 
@@ -278,9 +279,25 @@ def run_ours(args):
     pinned = [torch.from_numpy(c).pin_memory() for c in cand_host]
     d_stage = torch.empty_like(d_cands[0])
     best_pinned = torch.zeros(args.nimg * 2, dtype=torch.int64).pin_memory()
+    if world == 1:
+        # the host-buffer entry point of the C ABI itself: snes_batch_step_random(ctx, images, ..., cand /* host */, ...,
+        # best /* host */): candidates are copied to the device, the step runs, the winning records come back, the call
+        # returns when the stream has drained -- all inside the timed region
+        pinned_np = [p.numpy() for p in pinned]
+        best_np = best_pinned.numpy().view(engine.BEST_DTYPE)
+
+        def host_step(it):
+            p, i = opt.cursor.palette, opt.cursor.palette_index
+            best, _ = engine.batch_step_random(images, p, i, pinned_np[it])
+            best_np[:] = best
+            opt.cursor.advance(opt.config)
+            opt.iteration += 1
+    else:
+        def host_step(it):
+            opt.step_random_host(pinned[it], d_stage, best_pinned)
     for it in range(min(3, args.warmup)):
-        opt.step_random_host(pinned[it], d_stage, best_pinned)
-    ms_e2e = timed(lambda it: opt.step_random_host(pinned[it], d_stage, best_pinned), range(args.warmup, nsteps))
+        host_step(it)
+    ms_e2e = timed(host_step, range(args.warmup, nsteps))
     e2e_value = evals_per_step * args.steps / (ms_e2e * 1e-3)
 
     # ---- roofline of the dominant kernel ----
