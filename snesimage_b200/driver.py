@@ -133,6 +133,51 @@ class BatchOptimizer:
         return self._best.cpu().numpy().view(engine.BEST_DTYPE)
 
 
+def sweep_random(images: Sequence[engine.OptimizedImage], seed: int, sweep: int, ncand: int = 64) -> np.ndarray:
+    """Opt-in whole-sweep batching (TODO.md:33-35) -- NOT the reference's trajectory.
+
+    The reference improves one palette entry at a time, each against the state the previous one left.  Here every
+    entry's `ncand` random candidates are evaluated against ONE base state (C*S independent batches the GPU can run
+    back to back without waiting for accept decisions), then per image the best strictly-improving candidate of each
+    subpalette is tried in order of predicted gain and kept only if the image's real error() drops (subpalettes own
+    disjoint tiles, so their winners rarely interfere; the re-check makes the step monotone regardless).
+    Returns the error of every image after the sweep."""
+    cfg = images[0].config
+    C, S, nimg = cfg.subpalette_count, cfg.subpalette_size, len(images)
+    base = engine.batch_error(images)
+    winners = [[] for _ in range(nimg)]          # per image: (predicted error, subpalette, index, colour)
+    for p in range(C):
+        best_p = [None] * nimg
+        for i in range(S):
+            cand = np.stack([synth.candidates(seed * 1000003 + j, sweep * C * S + p * S + i, ncand) for j in range(nimg)])
+            r = engine.batch_eval_candidates(images, p, i, cand, want_scores=False)
+            for j in range(nimg):
+                err, k = float(r["best"]["err"][j]), int(r["best"]["idx"][j])
+                if k >= 0 and err < base[j] and (best_p[j] is None or err < best_p[j][0]):
+                    best_p[j] = (err, p, i, cand[j, k].copy())
+        for j in range(nimg):
+            if best_p[j] is not None:
+                winners[j].append(best_p[j])
+    out = np.array(base, dtype=np.float64)
+    for j, im in enumerate(images):
+        cur = out[j]
+        for err, p, i, colour in sorted(winners[j], key=lambda w: w[0]):
+            pal = im.palette
+            old = pal[p * S + i].copy()
+            pal[p * S + i] = colour
+            im.palette = pal
+            im.optimize()
+            e = im.error()
+            if e < cur:
+                cur = e
+            else:                                 # interfered with an earlier winner: take it back
+                pal[p * S + i] = old
+                im.palette = pal
+                im.optimize()
+        out[j] = cur
+    return out
+
+
 class HeadlessRunner:
     """`run()` of the reference without the window: initialize_tiles -> recalculate_palettes -> N
     iterations of the optimiser schedule -> JSON (lib.rs:851-853, 987-989, 889-933, 999-1003)."""

@@ -249,3 +249,31 @@ def test_tile_moves_match_oracle(ctx, kw):
     with pytest.raises(engine.SnesGpuError):
         engine.batch_eval_tile_moves([r.image], np.asarray([[(2000, 0)]], np.int32))
     r.image.close()
+
+
+@pytest.mark.gpu
+def test_whole_sweep_batching_is_monotone_and_consistent(ctx):
+    """Opt-in whole-sweep batching: not the reference's trajectory, so what is checked is what it
+    promises -- the error never rises, and the state it leaves is a state of the reference's model: the oracle, given the
+    same palette and tile assignment, derives the same palette_map and error."""
+    from snesimage_b200 import driver, engine
+    C, S = 3, 4
+    cfg = engine.Config(subpalette_count=C, subpalette_size=S)
+    rgbas = [synth.image(71 + j, "V") for j in range(2)]
+    imgs = [engine.OptimizedImage(ctx, r, cfg) for r in rgbas]
+    engine.batch_initialize_tiles(imgs)
+    engine.batch_recalculate_palettes(imgs)
+    before = engine.batch_error(imgs)
+    after = driver.sweep_random(imgs, seed=3, sweep=0, ncand=8)
+    assert np.all(after <= before)
+    assert np.any(after < before)
+    again = engine.batch_error(imgs)
+    assert np.array_equal(again, after)
+    for r, im in zip(rgbas, imgs):
+        o = ob.OracleImage(r, C, S)
+        o.tile_palettes = im.tile_palettes
+        o.palette = im.palette
+        o.optimize()
+        assert np.array_equal(o.palette_map, im.palette_map)
+        assert abs(o.error() - im.error()) <= 1e-8
+        im.close()
