@@ -119,6 +119,48 @@ def test_red_mean_formula_and_integer_key():
     assert key.max() < 2 ** 31
 
 
+def test_expanded_red_mean_key_and_rounding_rule_of_the_dither_kernel():
+    # snesimage_b200/csrc/dither.cuh evaluates the integer key with the target-only terms dropped,
+    #   key'' = C0 + A r - R (r^2 + b^2) - 4096 G g + C1 b + 2B (r b)   (int32, wrap-around arithmetic)
+    # and must rank the entries of a pixel exactly like the full key (first strict minimum).  Exhaustive over the
+    # corners and a random sample of (target, entry) pairs, in int32 with overflow wrapping like the GPU.
+    rng = np.random.RandomState(7)
+    corners = np.array([[r, g, b] for r in (0, 1, 127, 128, 254, 255) for g in (0, 128, 255) for b in (0, 1, 128, 255)])
+    tg = np.concatenate([corners, rng.randint(0, 256, (3000, 3))]).astype(np.int64)
+    en = np.concatenate([corners, rng.randint(0, 256, (3000, 3))]).astype(np.int64)
+    r, g, b = tg[:, None, 0], tg[:, None, 1], tg[:, None, 2]
+    R, G, B = en[None, :, 0], en[None, :, 1], en[None, :, 2]
+    key = (1024 + r + R) * (R - r) ** 2 + 2048 * (G - g) ** 2 + (1534 - r - R) * (B - b) ** 2
+    const = r ** 3 + 1024 * r ** 2 + 2048 * g ** 2 + 1534 * b ** 2 - r * b ** 2
+    C0 = (1024 + R) * R * R + 2048 * G * G + (1534 - R) * B * B
+    A = -R * R - 2048 * R - B * B
+    C1 = -2 * B * (1534 - R)
+    with np.errstate(over="ignore"):
+        i32 = lambda v: v.astype(np.int32)  # noqa: E731  (wraps modulo 2^32 like the device arithmetic)
+        k2 = i32(C0) + i32(A) * i32(r) + i32(-R) * i32(r * r + b * b) + i32(-4096 * G) * i32(g) + i32(C1) * i32(b) + i32(2 * B) * i32(r * b)
+    assert np.array_equal(k2.astype(np.int64), key - const)          # exact, no overflow in the final value
+    assert np.abs(key - const).max() < 2 ** 31 and np.abs(C0).max() < 2 ** 31
+    # ranking of 15-entry subpalettes: first strict minimum of key'' == first strict minimum of key
+    for trial in range(200):
+        sub = rng.choice(len(en), 15, replace=trial % 2 == 0)  # with replacement: duplicate entries -> ties
+        assert np.array_equal(np.argmin(key[:, sub], axis=1), np.argmin(k2[:, sub], axis=1))
+
+    # clamp(0, 255).round() (half away from zero, lib.rs:773-778) as truncate + exact-fraction test + integer clamp
+    eps = np.finfo(np.float64).eps
+    t = np.concatenate([rng.uniform(-300, 600, 20000), np.arange(-3, 259) + 0.5, np.arange(-3, 259) + 0.5 - 64 * eps,
+                        np.arange(-3, 259) - 0.5 + 64 * eps, [0.49999999999999994, 254.99999999999997, -0.0, 1e300, -1e300]])
+    c = np.clip(t, 0.0, 255.0)
+    want = np.where(c - np.floor(c) >= 0.5, np.floor(c) + 1, np.floor(c)).astype(np.int64)  # exact half-away rule for c >= 0
+    tz = np.trunc(np.clip(t, -2.0 ** 31, 2.0 ** 31 - 1))             # cvt.rzi.s32.f64 saturates
+    got = np.clip(tz + (t - tz >= 0.5), 0, 255).astype(np.int64)
+    assert np.array_equal(got, want)
+    for v in (0.5, 1.5, 2.5, 254.5, 0.49999999999999994, -0.5, 255.5):  # against the oracle's own rounding
+        col = np.array([[0, 0, 0], [0, 0, 1]], np.uint8)               # as_rgba blue 0 and 8
+        rounded = int(got[np.where(t == v)[0][0]]) if (t == v).any() else None
+        if rounded is not None:
+            assert ob.closest_color_index(col, [0.0, 0.0, v]) == (1 if abs(rounded - 8) < abs(rounded - 0) else 0)
+
+
 def test_closest_color_strict_first_min_and_rounding():
     colors = np.array([[0, 0, 0], [10, 10, 10], [10, 10, 10], [31, 31, 31]], np.uint8)
     assert ob.closest_color_index(colors, [82.0, 82.0, 82.0]) == 1          # tie between 1 and 2 -> lowest index
