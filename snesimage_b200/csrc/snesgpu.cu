@@ -77,6 +77,7 @@ struct snes_ctx {
     uint8_t *cand = nullptr;
     size_t img_cap = 0;
     ImgDev *d_imgs = nullptr;
+    ImgTm *d_imgtm = nullptr;   // tensor maps of the bound images, parallel to d_imgs
     KmScratch *d_km = nullptr;
     Best *best = nullptr;
     double *self_scores = nullptr;
@@ -97,8 +98,72 @@ struct snes_image {
     ImgDev dev{};
     KmScratch km{};
     void *slab = nullptr, *km_slab = nullptr;
+    ImgTm tm{};                  // TMA tensor maps over the slab (source pyramid per scale, own palette_map)
     std::vector<uint8_t> alpha;  // host copy of the alpha channel (as_json)
 };
+
+// ------------------------------------------------------------------------------------------------
+// TMA tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point: no libcuda link)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*tm_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tm_encode_fn tm_encoder() {
+    static tm_encode_fn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            fn = (tm_encode_fn)p;
+    }
+    return fn;
+}
+// rank-`rank` tensor of f32 (esize 4) or u32 (esize 0) elements at `base`: dims[] elements, strides[] bytes for dims 1.., box[] elements
+static int tm_make(CUtensorMap *out, const void *base, int esize, int rank, const uint64_t *dims, const uint64_t *strides, const uint32_t *box) {
+    tm_encode_fn enc = tm_encoder();
+    if (!enc) return fail(SNES_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t gd[5], gs[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; i++) {
+        gd[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+        if (i > 0) gs[i - 1] = strides[i - 1];
+    }
+    const CUresult r = enc(out, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT32, (cuuint32_t)rank, const_cast<void *>(base), gd,
+                           gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SNES_E_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return SNES_OK;
+}
+static uint32_t tm_box_rows(int s) { return (uint32_t)(((W >> s) < V3Smem::HB ? (W >> s) : V3Smem::HB) + 4); }
+// an image's own planes: source pyramid scale s as (D, D, 3) f32, palette_map as (256, 256) u8
+static int tm_make_image(ImgTm *tm, const ImgDev &dev) {
+    for (int s = 0; s < NSCALES; s++) {
+        const uint64_t D = W >> s, dims[3] = {D, D, 3}, strides[2] = {D * 4, D * D * 4};
+        const uint32_t box[3] = {(uint32_t)V3Smem::IP, tm_box_rows(s), 1};
+        RET(tm_make(&tm->src[s], dev.xyb_rm + 3 * (size_t)scale_off(s), 4, 3, dims, strides, box));
+    }
+    // palette_map rows as 4-pixel words (the conversion reads words; x coordinates are multiples of 4)
+    const uint64_t dims[2] = {W / 4, H}, strides[1] = {W};
+    const uint32_t box[2] = {V3Smem::RAWP, tm_box_rows(0)};
+    return tm_make(&tm->own, dev.map, 0, 2, dims, strides, box);
+}
+// an evaluation buffer: palette_maps (may be null) as (256, 256, E) u8, coarse pyramids per scale as (D, D, 3, E) f32
+static int tm_make_evals(EvalTm *tm, const uint8_t *maps, const float *xyb, int E) {
+    memset(tm, 0, sizeof(*tm));
+    if (maps) {
+        const uint64_t dims[3] = {W / 4, H, (uint64_t)E}, strides[2] = {W, (uint64_t)NPIX};
+        const uint32_t box[3] = {V3Smem::RAWP, tm_box_rows(0), 1};
+        RET(tm_make(&tm->t[0], maps, 0, 3, dims, strides, box));
+    }
+    for (int s = 1; s < NSCALES; s++) {
+        const uint64_t D = W >> s, dims[4] = {D, D, 3, (uint64_t)E}, strides[3] = {D * 4, D * D * 4, (uint64_t)EVAL_XYB_FLOATS * 4};
+        const uint32_t box[4] = {(uint32_t)V3Smem::IP, tm_box_rows(s), 1, 1};
+        RET(tm_make(&tm->t[s], xyb + 3 * (size_t)scale_off(s), 4, 4, dims, strides, box));
+    }
+    return SNES_OK;
+}
 
 static void prof_begin(snes_ctx *ctx, const char *name) {
     if (!ctx->profiling) return;
@@ -300,6 +365,8 @@ static void free_scratch(snes_ctx *ctx) {
     cudaFree(ctx->cents);
     cudaFree(ctx->cand);
     cudaFree(ctx->d_imgs);
+    cudaFree(ctx->d_imgtm);
+    ctx->d_imgtm = nullptr;
     cudaFree(ctx->d_km);
     cudaFree(ctx->best);
     cudaFree(ctx->self_scores);
@@ -450,6 +517,8 @@ static int ensure_imgs(snes_ctx *ctx, size_t n) {
     if (n <= ctx->img_cap) return SNES_OK;
     CK(cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->d_imgs);
+    cudaFree(ctx->d_imgtm);
+    ctx->d_imgtm = nullptr;
     cudaFree(ctx->d_km);
     cudaFree(ctx->best);
     cudaFree(ctx->self_scores);
@@ -464,6 +533,7 @@ static int ensure_imgs(snes_ctx *ctx, size_t n) {
     ctx->img_cap = 0;
     ctx->cached.clear();
     RET(dev_alloc(&ctx->d_imgs, n));
+    RET(dev_alloc(&ctx->d_imgtm, n));
     RET(dev_alloc(&ctx->d_km, n));
     RET(dev_alloc(&ctx->best, n));
     RET(dev_alloc(&ctx->self_scores, n));
@@ -486,7 +556,10 @@ static int bind_images(snes_ctx *ctx, snes_image *const *images, int nimg) {
     if ((int)ctx->cached.size() == nimg && memcmp(ctx->cached.data(), images, sizeof(snes_image *) * nimg) == 0) return SNES_OK;
     std::vector<ImgDev> h(nimg);
     for (int j = 0; j < nimg; j++) h[j] = images[j]->dev;
+    std::vector<ImgTm> htm(nimg);
+    for (int j = 0; j < nimg; j++) htm[j] = images[j]->tm;
     CK(cudaMemcpyAsync(ctx->d_imgs, h.data(), sizeof(ImgDev) * nimg, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_imgtm, htm.data(), sizeof(ImgTm) * nimg, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->cached.assign(images, images + nimg);
     return SNES_OK;
@@ -519,6 +592,10 @@ static int launch_scorer(snes_ctx *ctx, const FusedArgs &fa, int ec, const Fused
         va.nitems = 3 * ec;
         va.f2 = extra ? *extra : fa;
         va.nitems2 = extra ? 3 * extra_evals : 0;
+        va.imgtm = ctx->d_imgtm;
+        RET(tm_make_evals(&va.tm, fa.from_image ? nullptr : fa.maps, fa.xyb_rm, ec));
+        if (extra) RET(tm_make_evals(&va.tm2, extra->from_image ? nullptr : extra->maps, extra->xyb_rm, extra_evals));
+        else va.tm2 = va.tm;
         va.counter = ctx->v3_counter;
         va.hscratch = ctx->v3_scratch;
         const int items = 2 * (va.nitems + va.nitems2);   // every (evaluation, channel) is two work items
@@ -767,6 +844,7 @@ extern "C" int snes_image_new(snes_ctx *ctx, const uint8_t *rgba, int width, int
     cudaStream_t st = ctx->stream;
     int rc = SNES_OK;
     auto body = [&]() -> int {
+        RET(tm_make_image(&im->tm, im->dev));
         CK(cudaMemsetAsync(im->slab, 0, o_rm, st));  // tile_palettes, palette (Palette::new: all black), palette_map = 0
         CK(cudaMemsetAsync(b + o_tab, 0, sizeof(PalTables), st));
         CK(cudaMemsetAsync(b + o_err, 0, sizeof(double), st));
