@@ -103,8 +103,10 @@ __global__ void __launch_bounds__(256) k_assign_prepare(const ImgDev *imgs, int 
 // candidate do not serialise whole warps.
 constexpr int PYR_MAXJOBS = 1020;   // a multiple of the 5 pixels a block queues, so a refused block leaves no gap
 
+// MODE 0 (one integer key per affected pixel) is bound by the latency of its dependent loads: 64 registers for a fourth CTA
+// per SM pay (0.67 -> 0.59 ms per 4096 evaluations); the CIEDE2000 and full-pyramid modes are faster with their registers
 template <int MODE>
-__global__ void __launch_bounds__(256) k_assign_pyr(const ImgDev *imgs, const CandEntry *cents, int ncand, int e0, int S, int CS,
+__global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) k_assign_pyr(const ImgDev *imgs, const CandEntry *cents, int ncand, int e0, int S, int CS,
                                                     int ovr, uint8_t *maps, float *xyb_rm_base, const float *base_xyb) {
     __shared__ float s_lin[MAX_ENTRIES + 1][3];
     __shared__ float4 s_jobs[(MODE == 2) ? 1 : PYR_MAXJOBS];   // linear RGB + output offset of a queued pixel
