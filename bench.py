@@ -139,7 +139,7 @@ def run_reference(args):
         "gpu_launches": 0,
         "wall_s": time.perf_counter() - t_all,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ---- clocks ------------------------------------------------------------------------------------------
@@ -346,9 +346,31 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(cand_host[0].nbytes), "d2h_bytes_per_step": int(best_pinned.numel() * 8)},
             "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """Keep stdout for the one JSON line: everything else written to fd 1 from here on -- native libraries included (NCCL
+    prints its version banner there when NCCL_DEBUG is set in the environment) -- goes to stderr."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
@@ -363,6 +385,7 @@ def main():
     ap.add_argument("--cpu-evals", type=int, default=128)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
