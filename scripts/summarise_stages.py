@@ -10,8 +10,8 @@ import sys
 tag = sys.argv[1]
 UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
 TIME = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "second": 1.0}
-out = [f"# {tag}: ncu --set full --clock-control none, one launch per kernel (the longest of those captured), scripts/quick_bench.py 16 <mode> v3",
-       "# (16 images x 64 candidates = 1024 evaluations per launch; DRAM peak of this pool 6552.6 GB/s measured, MEASURED_PEAKS.json)",
+out = [f"# {tag}: ncu --set full --clock-control none, one launch per kernel (the longest of those captured), scripts/quick_bench.py 4 <mode> v3",
+       "# (4 images x 64 candidates = 256 evaluations per launch; DRAM peak of this pool 6552.6 GB/s measured, MEASURED_PEAKS.json)",
        f"{'mode':7s}{'kernel':34s}{'grid':>8s}{'ms':>9s}{'DRAM MB':>10s}{'DRAM GB/s':>11s}{'L2 MB':>10s}{'L2 GB/s':>10s}{'dram%':>7s}{'sm%':>6s}{'occ%':>6s}{'regs':>6s}{'IPC':>6s}"]
 for spec in sys.argv[2:]:
     mode, rep = spec.split("=")
