@@ -61,3 +61,14 @@ def test_lloyd_against_scipy(k, n, seed):
     cen, lab = vq.kmeans2(pts, pts[:k].copy(), iter=max(int(iters), 1) + 50, minit="matrix")
     assert np.abs(np.asarray(centres) - cen).max() < 1e-9
     assert np.array_equal(np.asarray(labels), lab)
+
+
+def test_srgb_eotf_against_iec_formula():
+    """yuvxyb linearises with the H.273 constants (alpha 1.0550107..., beta 0.0030412825...), which differ from the rounded
+    IEC 61966-2-1 ones (1.055, 0.04045) in the sixth digit: all 256 levels agree to 1e-5, and a gamma-2.2 curve would not."""
+    v = np.arange(256) / 255.0
+    iec = np.where(v <= 0.04045, v / 12.92, ((v + 0.055) / 1.055) ** 2.4)
+    ours = np.array([ob.lib().ora_srgb_eotf(float(np.float32(x))) for x in v])
+    assert np.abs(ours - iec).max() < 1e-5
+    assert np.abs(ours - v ** 2.2).max() > 5e-3
+    assert np.all(np.diff(ours) > 0)
