@@ -147,3 +147,24 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["metric"].startswith("candidate palette evals/sec") and "workload" in line["config"]
+
+
+def test_vertical_chain_thread_mapping_covers_every_plane_column_once():
+    """Index logic of k_score_v3's vertical pass (score_v3.cuh): role threads 0..63 take word t of the interleaved
+    (mu2, s22) row, i.e. (column t / 2, plane t % 2); threads 64..95 take column t - 64 of s12; lanes beyond a narrow
+    scale's width sit out.  Every (plane, column) of the 32-column block must be owned by exactly one thread, and a
+    warp's lanes must touch consecutive words."""
+    BW = 32
+    for D in (8, 16, 32, 64, 128, 256):
+        owned = []
+        for t in range(128):
+            if t < 2 * BW:
+                if (t >> 1) < D:
+                    owned.append((t & 1, t >> 1, ("h01", t)))
+            elif t < 3 * BW and t - 2 * BW < D:
+                owned.append((2, t - 2 * BW, ("h2", t - 2 * BW)))
+        want = {(pl, col) for pl in range(3) for col in range(min(D, BW))}
+        assert sorted((pl, col) for pl, col, _ in owned) == sorted(want)
+        for warp in range(3):
+            words = [w for _, _, (buf, w) in owned if (buf == "h01" and w // 32 == warp) or (buf == "h2" and warp == 2)]
+            assert not words or words == list(range(words[0], words[0] + len(words)))   # consecutive words: one wavefront per access
