@@ -2,16 +2,19 @@
 """bench.py -- candidate palette evaluations per second (BASELINE.json metric).
 
 Workload (BASELINE.json configs[4]): 64 synthetic 256x256 images, 8 subpalettes x 15
-colours, RGB distance, no dither.  One step = one `optimize_palette_entry_random` for every image:
-error() + 64 candidate evaluations (optimize() + error() each) per image per GPU + argmin + accept +
-optimize().  Weak scaling: every rank evaluates 64 candidates per image (64*N per image in total); the only
-exchange is the all-gather argmin of 16 bytes per image.
+colours, RGB distance, no dither, 64 random candidates per image and step = 4096 candidate evaluations per step IN
+TOTAL, whatever the number of GPUs (strong scaling).  One step = one `optimize_palette_entry_random` for every image:
+error() + 64 x (optimize() + error()) + argmin + accept + optimize() (lib.rs:191-240).  At N > 1 the job is sharded as
+driver.plan_shards says: with 64 images every rank owns 64/N images outright (nothing replicated); the exchange per
+step is the all-gather of the 16-byte (error, index) records over NCCL.
 
   value     whole-job candidate evaluations / s, candidate lists resident in HBM (device-timed, max over ranks)
-  e2e       the same step through the host-buffer entry point of the C ABI (snes_batch_step_random): candidate H2D +
-            winning records D2H inside every call (N > 1: pinned host buffers around the sharded device-pointer step)
+  e2e       the same step through the host-buffer entry points of the C ABI: candidate H2D + winning records D2H inside
+            every call (N = 1: snes_batch_step_random; N > 1: snes_batch_step_random_shard_begin / _end around the
+            all-gather)
   roofline  the dominant kernel's algorithmic bytes / its CUDA-event time, against MEASURED_PEAKS.json
   cpu_baseline  the CPU oracle (C restatement of the reference) on this box's host cores, bounded sample
+  outside the headline's timed region: `weak` and `candidate_sharded` (N > 1), `modes` and `configs` (N = 1)
 
 `--impl reference` times the CPU restatement of the reference's own loop on all host cores (the Rust
 crate cannot be built in this image: no cargo/rustc, un-vendored crates -- see DESIGN.md).
@@ -39,7 +42,8 @@ NIMG, NCAND = 64, 64
 B_ALG = 3_548_624
 B_S2 = 3_219_560      # scoring share of B_ALG: 65,536 + 8,192 + 3,144,960 + 872
 B_MIN = 403_664
-WORKLOAD = "cfg5: 64 synthetic 256x256 images (V family, seeds 0..63) x 64 random candidates/image/GPU per step, 8x15, RGB, no dither"
+WORKLOAD = ("cfg5: 64 synthetic 256x256 images (V family, seeds 0..63) x 64 random candidates per image = 4096 candidate "
+            "evaluations per step in total, 8x15, RGB, no dither")
 
 
 def host_cores() -> int:
@@ -47,6 +51,17 @@ def host_cores() -> int:
         return len(os.sched_getaffinity(0))
     except AttributeError:
         return os.cpu_count() or 1
+
+
+def build_config(args, world: int) -> dict:
+    """The `config` object of the JSON line -- one function for both arms, so they name the same workload key by key."""
+    groups = max(d for d in range(1, world + 1) if world % d == 0 and d <= args.nimg)
+    return {"workload": WORKLOAD, "subpalettes": C, "colours": S, "metric_mode": "rgb", "dither": False,
+            "images": args.nimg, "candidates_per_image": args.ncand, "evals_per_step": args.nimg * args.ncand,
+            "parallelism": f"{groups} image groups x {world // groups} candidate slices over {world} GPU(s), all-gather argmin (16 B/image)",
+            "l2": "inputs larger than L2: per step and GPU 3.4 MB of source planes per image held + 326 KB of intermediates per "
+                  "evaluation (>= 190 MB at 8 GPUs, 1.5 GB at one)",
+            "bookkeeping_evals_per_step_not_counted": 2 * args.nimg, "chunk": args.chunk}
 
 
 # ---- CPU side: the oracle as the reference's stand-in --------------------------------------------------
@@ -129,9 +144,9 @@ def run_reference(args):
     value = evals / total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "subpalettes": C, "colours": S, "metric_mode": "rgb", "dither": False},
+        "config": build_config(args, max(1, args.gpus)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{cores} processes x {per_proc} candidate evaluations per step (optimize()+error() each), "
                                    f"C restatement of lib.rs + crates (oracle/), gcc -O2; the Rust reference cannot be built here"},
@@ -177,7 +192,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.01)
+            self._stop.wait(0.005)
 
     def start(self):
         if self.nv:
@@ -201,10 +216,52 @@ def measured_peaks():
 
 
 # ---- GPU arm -----------------------------------------------------------------------------------------
+class Job:
+    """One sharded optimiser job on this rank: its images (created and k-means-initialised), its BatchOptimizer and the
+    candidate lists of every step, on the device and in pinned host memory."""
+
+    def __init__(self, ctx, dev, rank, world, nimg, ncand_total, nsteps, mode="hybrid", cfg_kw=None, family="V"):
+        import torch
+        from snesimage_b200 import driver, engine, synth
+        self.torch, self.dev, self.world = torch, dev, world
+        self.plan = driver.plan_shards(nimg, rank, world, mode)
+        cfg = engine.Config(**{"subpalette_count": C, "subpalette_size": S, **(cfg_kw or {})})
+        self.images = [engine.OptimizedImage(ctx, synth.image(s, family), cfg) for s in range(self.plan.img_lo, self.plan.img_hi)]
+        engine.batch_initialize_tiles(self.images)
+        engine.batch_recalculate_palettes(self.images)
+        self.opt = driver.BatchOptimizer(ctx, self.images, plan=self.plan, seed=0)
+        self.ncand_total = ncand_total
+        self.cand_host = []
+        for it in range(nsteps):
+            self.opt.iteration = it
+            self.cand_host.append(self.opt.candidates_host(ncand_total))
+        self.opt.iteration = 0
+        self.d_cands = [torch.from_numpy(c).to(dev) for c in self.cand_host]
+        self.pinned = [torch.from_numpy(c).pin_memory().numpy() for c in self.cand_host]
+        self.evals_per_step = nimg * ncand_total
+        torch.cuda.synchronize()
+
+    def step_dev(self, it):
+        self.opt.step_random_dev(self.d_cands[it], self.ncand_total)
+
+    def step_host(self, it):
+        self.opt.step_random_host(self.pinned[it])
+
+    def checksum(self) -> int:
+        h = 0xcbf29ce484222325
+        for v in self.opt.state_checksums():
+            h = ((h ^ v) * 0x100000001b3) & 0xFFFFFFFFFFFFFFFF
+        return h
+
+    def close(self):
+        for im in self.images:
+            im.close()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from snesimage_b200 import driver, engine, synth
+    from snesimage_b200 import _build, engine
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -223,24 +280,6 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-
-    ctx = engine.Context(local, chunk=args.chunk)
-    cfg = engine.Config(subpalette_count=C, subpalette_size=S)
-    images = [engine.OptimizedImage(ctx, synth.image(s, "V"), cfg) for s in range(args.nimg)]
-    engine.batch_initialize_tiles(images)
-    engine.batch_recalculate_palettes(images)
-    opt = driver.BatchOptimizer(ctx, images, rank=rank, world=world, group=None, seed=0)
-
-    ncand_total = args.ncand * world
-    nsteps = args.warmup + args.steps
-    # pre-generate every step's candidate list: (steps, nimg, ncand_total, 3)
-    cand_host = []
-    for it in range(nsteps):
-        opt.iteration = it
-        cand_host.append(opt.candidates_host(ncand_total))
-    opt.iteration = 0
-    d_cands = [torch.from_numpy(c).to(dev) for c in cand_host]
-    torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -261,46 +300,44 @@ def run_ours(args):
         barrier()
         return float(ms.item())
 
-    # ---- device-resident arm (value) ----
+    def gather_checksums(job):
+        mine = (rank, job.plan.group, f"{job.checksum():016x}")
+        if world == 1:
+            return [mine]
+        out = [None] * world
+        dist.all_gather_object(out, mine)
+        return out
+
+    ctx = engine.Context(local, chunk=args.chunk)
+    nsteps = args.warmup + args.steps
+
+    # ---- headline: cfg5 as written, 4096 evaluations per step in total, sharded (strong scaling) ----
+    job = Job(ctx, dev, rank, world, args.nimg, args.ncand, nsteps)
     for it in range(args.warmup):
-        opt.step_random_dev(d_cands[it], ncand_total)
+        job.step_dev(it)
     clocks = ClockSampler(local)
     launches0 = ctx.kernel_launches
     ctx.profile_begin()
     clocks.start()
-    ms = timed(lambda it: opt.step_random_dev(d_cands[it], ncand_total), range(args.warmup, nsteps))
+    ms = timed(job.step_dev, range(args.warmup, nsteps))
     clock_info = clocks.stop()
     prof = ctx.profile_end()
     launches = ctx.kernel_launches - launches0
-    evals_per_step = args.nimg * ncand_total
+    evals_per_step = job.evals_per_step
     value = evals_per_step * args.steps / (ms * 1e-3)
 
-    # ---- host-buffer arm (e2e): same steps again from pinned host memory ----
-    pinned = [torch.from_numpy(c).pin_memory() for c in cand_host]
-    d_stage = torch.empty_like(d_cands[0])
-    best_pinned = torch.zeros(args.nimg * 2, dtype=torch.int64).pin_memory()
-    if world == 1:
-        # the host-buffer entry point of the C ABI itself: snes_batch_step_random(ctx, images, ..., cand /* host */, ...,
-        # best /* host */): candidates are copied to the device, the step runs, the winning records come back, the call
-        # returns when the stream has drained -- all inside the timed region
-        pinned_np = [p.numpy() for p in pinned]
-        best_np = best_pinned.numpy().view(engine.BEST_DTYPE)
-
-        def host_step(it):
-            p, i = opt.cursor.palette, opt.cursor.palette_index
-            best, _ = engine.batch_step_random(images, p, i, pinned_np[it])
-            best_np[:] = best
-            opt.cursor.advance(opt.config)
-            opt.iteration += 1
-    else:
-        def host_step(it):
-            opt.step_random_host(pinned[it], d_stage, best_pinned)
+    # ---- host-buffer arm (e2e): the same steps again from pinned host memory through the C ABI's host entry points ----
     for it in range(min(3, args.warmup)):
-        host_step(it)
-    ms_e2e = timed(host_step, range(args.warmup, nsteps))
+        job.step_host(it)
+    ms_e2e = timed(job.step_host, range(args.warmup, nsteps))
     e2e_value = evals_per_step * args.steps / (ms_e2e * 1e-3)
+    sums = gather_checksums(job)
+    h2d = int(job.cand_host[0].nbytes)
+    d2h = int(job.plan.nloc * 16)
+    nloc = job.plan.nloc
+    plan_text = job.plan.describe()
 
-    # ---- roofline of the dominant kernel ----
+    # ---- roofline of the dominant kernel (this rank's launches) ----
     # Algorithmic bytes per evaluation: S1 = assignment (source RGBA8 + tile/palette tables +
     # palette_map write), S2 = scoring (palette_map + alpha mask + 36 B of source planes per scale-pixel + partial sums).
     peak, peak_src = measured_peaks()
@@ -309,46 +346,157 @@ def run_ours(args):
     roofline = None
     if top[0]:
         name, st = top
-        # every launch of the scorer covers one chunk of evaluations (bookkeeping error() launches are small ones);
-        # evaluations it processed in the timed region = candidates + the per-step error() of each image
-        scored = (args.nimg * args.ncand + args.nimg) * args.steps
+        # every launch of the scorer covers one chunk of evaluations; evaluations this rank's scorer processed in the
+        # timed region = its candidates + the per-step error() of each of its images
+        from snesimage_b200 import driver
+        lo, hi = driver.shard_bounds(args.ncand, job.plan.slice, job.plan.cand_ranks)
+        scored = (nloc * (hi - lo) + nloc) * args.steps
         alg_bytes = B_S2 if name.startswith("k_score") else B_ALG
         per_launch_bytes = alg_bytes * scored / st["n"]
         achieved = alg_bytes * scored / (st["ms"] * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_note = None, None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
                 tj = json.load(f)
-            if tj.get("kernel", "").split("<")[0] == name.split("<")[0]:
+            if tj.get("kernel", "").split("<")[0] != name.split("<")[0]:
+                traffic_note = "profiles/roofline_traffic.json describes another kernel"
+            elif tj.get("scorer_source_sha256") != _build.scorer_source_hash():
+                traffic_note = "profiles/roofline_traffic.json was captured from other scorer sources than the tree's: not reported"
+            else:
                 traffic = tj["dram_bytes_per_eval"] * scored / st["n"]
+                traffic_note = "ncu --set full capture of the same sources (profiles/roofline_traffic.json), scaled to this launch size"
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "traffic_source": traffic_note,
                     "kernel": name, "kernel_launches": st["n"], "kernel_ms_per_launch": st["ms"] / st["n"],
                     "kernel_share_of_gpu_time": st["ms"] / max(1e-9, total_ms),
                     "alg_bytes_per_eval": alg_bytes, "alg_bytes_per_launch": per_launch_bytes, "peak_source": peak_src,
                     "whole_path": {"alg_bytes_per_eval": B_ALG, "achieved": B_ALG * scored / (total_ms * 1e-3) / 1e9,
                                    "frac": B_ALG * scored / (total_ms * 1e-3) / 1e9 / peak, "gpu_ms_per_step": total_ms / args.steps},
                     "unique_bytes_per_eval": B_MIN,
-                    "note": "the scorer is FP32/FP64 issue-bound (recursive-Gaussian chains), not HBM-bound: see DESIGN.md for the instruction roofline",
+                    "note": "per GPU (rank 0's launches); the scorer is FP32/FP64 issue-bound (recursive-Gaussian chains), not HBM-bound: see DESIGN.md",
                     "kernels": prof}
+    job.close()
+
+    # ---- outside the headline's timed region -------------------------------------------------------------------------
+    extras = {}
+    if not args.no_extras and world > 1:
+        # the same 4096 evaluations per step with the round-1 layout (every rank holds all 64 images and evaluates a slice
+        # of each image's candidates): what replicating the per-image work costs
+        j2 = Job(ctx, dev, rank, world, args.nimg, args.ncand, nsteps, mode="candidates")
+        for it in range(args.warmup):
+            j2.step_dev(it)
+        ms2 = timed(j2.step_dev, range(args.warmup, nsteps))
+        sums2 = gather_checksums(j2)
+        extras["candidate_sharded"] = {"value": j2.evals_per_step * args.steps / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / args.steps,
+                                       "scaling": "strong", "parallelism": j2.plan.describe(),
+                                       "replicas_identical": len({c for _, _, c in sums2}) == 1}
+        j2.close()
+        # weak scaling as in round 1: 64 candidates per image AND GPU (64 x N per image), every rank holds all images
+        j3 = Job(ctx, dev, rank, world, args.nimg, args.ncand * world, nsteps, mode="candidates")
+        for it in range(args.warmup):
+            j3.step_dev(it)
+        ms3 = timed(j3.step_dev, range(args.warmup, nsteps))
+        extras["weak"] = {"value": j3.evals_per_step * args.steps / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3 / args.steps,
+                          "scaling": "weak", "evals_per_step": j3.evals_per_step, "parallelism": j3.plan.describe()}
+        j3.close()
+    if not args.no_extras and world == 1:
+        extras["modes"] = measure_modes(ctx, dev, args)
+        extras["configs"] = measure_configs(ctx)
 
     if rank == 0:
+        groups = {}
+        for r, g, c in sums:
+            groups.setdefault(g, set()).add(c)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "subpalettes": C, "colours": S, "metric_mode": "rgb", "dither": False,
-                       "images": args.nimg, "candidates_per_image_per_gpu": args.ncand, "evals_per_step": evals_per_step,
-                       "parallelism": f"candidate-sharded x{world}, all-gather argmin (16 B/image)",
-                       "l2": "inputs larger than L2: 64 images x 3.4 MB of source planes + per-evaluation intermediates (GBs per step)",
-                       "bookkeeping_evals_per_step_not_counted": 2 * args.nimg, "chunk": args.chunk},
+            "config": build_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": int(cand_host[0].nbytes), "d2h_bytes_per_step": int(best_pinned.numel() * 8)},
+                    "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                    "entry_points": "snes_batch_step_random" if world == 1 else "snes_batch_step_random_shard_begin + all_gather + snes_batch_step_random_shard_end"},
             "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "sharding": {"plan": plan_text, "images_per_rank": nloc,
+                         "state_checksums": [{"rank": r, "image_group": g, "fnv1a64": c} for r, g, c in sums],
+                         "replicas_identical": all(len(v) == 1 for v in groups.values())},
         }
+        line.update(extras)
         _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_modes(ctx, dev, args) -> dict:
+    """Device-timed step of the four reference modes on 64 images (one GPU): evaluations per second and the CUDA-event
+    time of every kernel of a step.  rgb / lab / dither: optimize_palette_entry_random with 64 candidates; nes: the 56
+    NES colours (lib.rs:242-284)."""
+    import torch
+    from snesimage_b200 import engine
+    modes = {"rgb": {}, "lab": {"perceptual_palettes": True, "subpalette_count": 4, "subpalette_size": 7},
+             "dither": {"dither": True}, "nes": {"nes": True, "dither": True, "subpalette_count": 4, "subpalette_size": 3}}
+    out = {}
+    warm, reps = 2, 4
+    for name, kw in modes.items():
+        job = Job(ctx, dev, 0, 1, args.nimg, args.ncand, warm + reps, cfg_kw=kw)
+        nes = bool(kw.get("nes"))
+        per_step = args.nimg * (56 if nes else args.ncand)
+
+        def step(it):
+            if nes:
+                engine.batch_step_nes(job.images, it % kw["subpalette_count"], it % kw["subpalette_size"])
+            else:
+                job.step_dev(it)
+        for it in range(warm):
+            step(it)
+        torch.cuda.synchronize()
+        ctx.profile_begin()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for it in range(warm, warm + reps):
+            step(it)
+        e1.record()
+        torch.cuda.synchronize()
+        prof = ctx.profile_end()
+        ms = e0.elapsed_time(e1) / reps
+        cfg = job.images[0].config
+        out[name] = {"value": per_step / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "evals_per_step": per_step,
+                     "subpalettes": cfg.subpalette_count, "colours": cfg.subpalette_size,
+                     "kernel_ms_per_step": {k: round(v["ms"] / reps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
+        job.close()
+    return out
+
+
+def measure_configs(ctx, iters: int = 100) -> dict:
+    """BASELINE.json configs[0..3] the way the reference is used: ONE picture, k-means init + tile assignment, then 100
+    iterations of the schedule of run() (lib.rs:889-933) through the headless driver; wall clock around synchronous calls."""
+    from snesimage_b200 import driver, engine, synth
+    cfgs = {"cfg1": dict(subpalette_count=8, subpalette_size=15),
+            "cfg2": dict(subpalette_count=4, subpalette_size=7, perceptual_palettes=True),
+            "cfg3": dict(subpalette_count=8, subpalette_size=15, dither=True),
+            "cfg4": dict(subpalette_count=4, subpalette_size=3, nes=True, dither=True)}
+    out = {}
+    rgba = synth.image(0, "V")
+    for name, kw in cfgs.items():
+        cfg = engine.Config(**kw)
+        r = driver.HeadlessRunner(ctx, rgba, cfg, seed=0, ncand=64)
+        t0 = time.perf_counter()
+        r.initialize()
+        ctx.synchronize()
+        t1 = time.perf_counter()
+        e0 = r.image.error()
+        r.iterate(3)
+        ctx.synchronize()
+        t2 = time.perf_counter()
+        r.iterate(iters)
+        ctx.synchronize()
+        t3 = time.perf_counter()
+        per_iter = 56 if cfg.nes else 64
+        out[name] = {"init_ms": 1e3 * (t1 - t0), "ms_per_iteration": 1e3 * (t3 - t2) / iters, "iterations": iters,
+                     "candidate_evals_per_s": iters * per_iter / (t3 - t2), "candidates_per_iteration": per_iter,
+                     "error_start": e0, "error_end": r.image.error(), "config": kw}
+        r.image.close()
+    return out
 
 
 _RESULT_FD = None
@@ -373,6 +521,12 @@ def _emit(line: dict):
         os.write(_RESULT_FD, data)
 
 
+def relaunch_command(args_gpus: int, argv) -> list:
+    """`python bench.py --gpus N` outside torchrun: the command that runs the same arguments under torch.distributed.run."""
+    return [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args_gpus}", "--master-addr", "127.0.0.1",
+            "--master-port", os.environ.get("BENCH_MASTER_PORT", "29517"), os.path.abspath(__file__)] + list(argv)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -384,18 +538,22 @@ def main():
     ap.add_argument("--chunk", type=int, default=4096)
     ap.add_argument("--cpu-evals", type=int, default=128)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the measurements outside the headline (modes, configs, weak, candidate_sharded)")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "ours" and args.gpus > 1 and world == 1:
+        # convenience: relaunch under torchrun.  Done BEFORE stdout is claimed, so the children inherit the real stdout
+        # and rank 0's JSON line lands there.
+        import subprocess
+        launcher = os.environ.get("BENCH_LAUNCHER")   # tests substitute a stub for torch.distributed.run
+        cmd = relaunch_command(args.gpus, sys.argv[1:])
+        if launcher:
+            cmd = [sys.executable, launcher] + cmd[3:]
+        raise SystemExit(subprocess.call(cmd))
     _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.gpus > 1 and world == 1:
-        # convenience: relaunch under torchrun
-        import subprocess
-        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
-               "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
-        raise SystemExit(subprocess.call(cmd))
     run_ours(args)
 
 

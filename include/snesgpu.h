@@ -74,12 +74,12 @@ int snes_ctx_synchronize(snes_ctx *ctx);
  * (at most cap-1 bytes + NUL; *len = full length). */
 int snes_ctx_profile_begin(snes_ctx *ctx);
 int snes_ctx_profile_end(snes_ctx *ctx, char *buf, size_t cap, size_t *len);
-/* kernel selection (all variants give the same results; kept switchable for A/B checks):
- *   fused             3 = k_score_v3 (default: persistent 4-warp CTAs, packed-f32 horizontal pass), 2 = k_score_v2,
- *                     1 = k_score_fused (all three keep the blur planes in shared memory); 0 = multi-kernel pipeline via HBM
- *   block_width       column block of k_score_fused, 16 or 32
+/* kernel selection (both scorers give the same f32 planes; kept switchable for A/B checks):
+ *   fused             3 = k_score_v3 (default: persistent 4-warp CTAs, TMA staging, packed-f32 horizontal pass),
+ *                     2 = k_score_v2 (its predecessor); anything else is refused
+ *   block_width       ignored (the column block is 32)
  *   delta_assign != 0 without dithering, a candidate re-decides only the pixels its entry can change (default)
- * Env overrides at context creation: SNESGPU_FUSED, SNESGPU_BW, SNESGPU_DELTA. */
+ * Env overrides at context creation: SNESGPU_FUSED, SNESGPU_DELTA. */
 int snes_ctx_set_scorer(snes_ctx *ctx, int fused, int block_width, int delta_assign);
 /* how many candidate evaluations have their scratch live at once (default 2048, env SNESGPU_CHUNK) */
 int snes_ctx_set_chunk(snes_ctx *ctx, int evaluations);
@@ -112,6 +112,8 @@ int snes_image_get_tile_palettes(snes_image *im, uint8_t *out /* 1024 */);
 int snes_image_set_tile_palettes(snes_image *im, const uint8_t *in);
 int snes_image_get_palette_map(snes_image *im, uint8_t *out /* 65536 */);
 int snes_image_set_palette_map(snes_image *im, const uint8_t *in);
+/* 64-bit FNV-1a over palette, tile_palettes and palette_map: replicas of an image on different ranks must agree on it */
+int snes_image_state_checksum(snes_image *im, uint64_t *out);
 
 /* ---- the same methods over a batch of images (independent OptimizedImages sharing one Config) -- */
 int snes_batch_initialize_tiles(snes_ctx *ctx, snes_image *const *images, int nimg);     /* lib.rs:79-189 */
@@ -140,19 +142,44 @@ int snes_batch_eval_candidates_dev(snes_ctx *ctx, snes_image *const *images, int
 int snes_batch_error_eval_candidates_dev(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
                                          const uint8_t *d_cand, int ncand, int cand_idx_base, double *d_scores,
                                          snes_best *d_best);
+/* The same for a rank of a candidate-sharded job: d_cand_all holds the full list, ncand_all candidates per image,
+ * identical on every rank; this rank evaluates candidates [cand_lo, cand_lo + ncand) of every image in place (no copy of
+ * the slice) and reports indices into the full list.  ncand == 0 (more ranks than candidates) is allowed: error() still
+ * runs and the records carry idx = -1, which never wins snes_merge_best_dev. */
+int snes_batch_error_eval_candidates_slice_dev(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
+                                               const uint8_t *d_cand_all, int ncand_all, int cand_lo, int ncand,
+                                               double *d_scores, snes_best *d_best);
 /* Accept rule of lib.rs:199,216-219,236-237 applied per image after the (possibly cross-rank) argmin:
  * if best[j].err < current error of image j, entry (palette,index) becomes cand_all[j][best[j].idx] and
  * the image is re-optimised; the image's cached error is updated.  d_cand_all holds ncand_all candidates
  * per image (the full, unsharded list).  Asynchronous on the context's stream. */
 int snes_batch_apply_best_dev(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
                               const uint8_t *d_cand_all, int ncand_all, const snes_best *d_best);
-/* Cross-rank argmin after an all-gather of every rank's best[nimg]: d_gathered is [nranks][nimg] with global
- * candidate indices; d_out[j] = lexicographic minimum of (err, idx) over ranks (lib.rs:216 for any rank count). */
-int snes_merge_best_dev(snes_ctx *ctx, const snes_best *d_gathered, int nranks, int nimg, snes_best *d_out);
+/* Cross-rank argmin after an all-gather of every rank's best records: rank r's nimg records start at
+ * d_gathered + r * rank_stride (rank_stride >= nimg; indices are already global); d_out[j] = lexicographic minimum of
+ * (err, idx) over the nranks ranks, records with idx < 0 never winning (lib.rs:216 for any rank count). */
+int snes_merge_best_dev(snes_ctx *ctx, const snes_best *d_gathered, int nranks, int rank_stride, int nimg, snes_best *d_out);
 /* Host-buffer convenience for one whole optimiser step over many images (eval + argmin + accept). */
 int snes_batch_step_random(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
                            const uint8_t *cand /* nimg*ncand*3 */, int ncand, snes_best *best /* optional */,
                            double *errors_after /* nimg, optional */);
+
+/* One optimize_palette_entry_random over a batch, sharded over the GPUs of one box, host buffers in and out (one process
+ * per GPU).  The exchange in the middle -- an all-gather of every rank's d_best_local, 16 bytes per image
+ * -- belongs to the caller's process group (NCCL); the library provides the two halves around it:
+ *   _begin  copies cand (host, nimg * ncand_all * 3, identical on the ranks that share these images) to the device, runs
+ *           error() and this rank's candidate slice [cand_lo, cand_lo + ncand), leaves nimg records in d_best_local
+ *           (device memory of the caller, e.g. the send buffer of the all-gather).  Asynchronous on the context's stream.
+ *   _end    d_gathered: the records of the nranks ranks that share these images, rank r at d_gathered + r * rank_stride;
+ *           lexicographic merge (lib.rs:216 for any rank count), accept, optimize(); best[nimg] / errors_after[nimg]
+ *           (host, optional) receive the merged records / error() of the new state; returns when the stream has drained.
+ * Device-pointer candidate lists (the *_dev entry points) must hold components <= 32: larger values are clamped for the
+ * evaluation, never applied, and reported by the next snes_ctx_synchronize() as SNES_E_INVALID. */
+int snes_batch_step_random_shard_begin(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
+                                       const uint8_t *cand, int ncand_all, int cand_lo, int ncand, snes_best *d_best_local);
+int snes_batch_step_random_shard_end(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
+                                     const snes_best *d_gathered, int nranks, int rank_stride, snes_best *best,
+                                     double *errors_after);
 
 /* optimize_palette_entry_nes / _channel for every image of a batch (lib.rs:242-284, 286-328) */
 int snes_batch_step_nes(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index, snes_best *best,

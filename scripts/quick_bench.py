@@ -19,7 +19,7 @@ for name in modes:
     engine.batch_initialize_tiles(imgs)
     engine.batch_recalculate_palettes(imgs)
     cand = np.stack([synth.candidates(s, 0, ncand) for s in range(nimg)])
-    variants = [("pipeline", 0, 32, 256), ("v3", 3, 32, 4096), ("v2", 2, 32, 4096), ("fused32", 1, 32, 4096), ("fused16", 1, 16, 4096), ("fused32/c512", 1, 32, 512)]
+    variants = [("v3", 3, 32, 4096), ("v2", 2, 32, 4096)]
     if len(sys.argv) > 3:
         variants = [v for v in variants if v[0] in sys.argv[3].split(",")]
     for label, fused, bw, chunk in variants:

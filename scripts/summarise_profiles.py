@@ -60,7 +60,10 @@ def nbytes(x):
     return float(x["value"]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[x["unit"]]
 
 
-j = {"kernel": "k_score_v3", "dram_bytes_per_eval": (nbytes(d["dram__bytes_read.sum"]) + nbytes(d["dram__bytes_write.sum"])) / evals,
+sys.path.insert(0, ".")
+from snesimage_b200 import _build  # noqa: E402
+
+j = {"kernel": "k_score_v3", "scorer_source_sha256": _build.scorer_source_hash(), "dram_bytes_per_eval": (nbytes(d["dram__bytes_read.sum"]) + nbytes(d["dram__bytes_write.sum"])) / evals,
      "source": f"ncu --set full --clock-control none, one persistent k_score_v3 launch over {evals} evaluations, profiles/{tag}_ncu_k_score_v3_raw_subset.json: "
                f"dram__bytes_read.sum {nbytes(d['dram__bytes_read.sum']) / 1e9:.4f} GB + dram__bytes_write.sum {nbytes(d['dram__bytes_write.sum']) / 1e6:.3f} MB",
      "inst_executed_per_eval": float(d["smsp__inst_executed.sum"]["value"]) / evals,

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libsnesgpu.so")
 SOURCES = ["snesgpu.cu"]
-HEADERS = ["common.cuh", "kernels.cuh", "lab.cuh", "dither.cuh", "kmeans.cuh", "score_fused.cuh", "score_v2.cuh", "score_v3.cuh", "assign_delta.cuh", os.path.join("..", "..", "include", "snesgpu.h")]
+HEADERS = ["common.cuh", "kernels.cuh", "lab.cuh", "dither.cuh", "kmeans.cuh", "score_common.cuh", "score_v2.cuh", "score_v3.cuh", "assign_delta.cuh", os.path.join("..", "..", "include", "snesgpu.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
@@ -34,6 +34,17 @@ def is_stale() -> bool:
     t = os.path.getmtime(SO)
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def scorer_source_hash() -> str:
+    """sha256 over the sources that define k_score_v3: profiles/roofline_traffic.json records it, bench.py reports the
+    file's DRAM traffic only while it still describes the kernel in the tree."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("common.cuh", "kernels.cuh", "score_common.cuh", "score_v2.cuh", "score_v3.cuh"):
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:

@@ -16,9 +16,8 @@ constexpr int NTILES = 1024;
 constexpr int NSCALES = 6;
 constexpr int TOTPIX = 87360;              // 65536+16384+4096+1024+256+64
 constexpr int EVAL_XYB_FLOATS = 3 * TOTPIX;  // positive-XYB pyramid of one evaluation
-constexpr int NSEG = 8;                    // <= 8 column segments (warps) per plane row
 constexpr int NSUMS = 6;                   // ssim d, d^4; edge artifact, artifact^4, detail_lost, detail_lost^4
-constexpr int PART_DOUBLES = NSCALES * 3 * NSEG * NSUMS;
+constexpr int PART_DOUBLES = NSCALES * 3 * NSUMS;  // partial sums of one evaluation: [scale][channel][NSUMS]
 constexpr int MAX_ENTRIES = 256;           // sub_count * sub_size
 constexpr int BLACK = 256;                 // table slot of a transparent (rendered black) pixel
 constexpr int GI_BLACK = 255;              // transparent pixel in a gi-format scratch map (needs C*S <= 255)

@@ -1,5 +1,6 @@
-// Device kernels of libsnesgpu (sm_100a): the candidate-evaluation pipeline
-//   k_tables -> k_assign_* -> k_pyramid -> k_blur_h -> k_blur_v -> k_pool -> k_argmin
+// Device kernels of libsnesgpu (sm_100a) around the scorer: palette tables, the full-search assignment, the XYB
+// pyramid, the source-side blur planes built once per image, argmin / merge / accept.
+//   candidate step: k_tables -> k_assign_* (assign_delta.cuh, dither.cuh) -> k_score_v3 -> k_pool_fused -> k_argmin
 // All of it is HBM/L2-bound byte, integer and f32 stencil work; no stage is a dense contraction,
 // so no tensor cores.  Each kernel cites the reference lines (lib.rs) or the crate routine it covers.
 #pragma once
@@ -27,8 +28,13 @@ __device__ __forceinline__ void fill_entry(uint8_t r5, uint8_t g5, uint8_t b5, u
     lin_to_pxyb(lin[0], lin[1], lin[2], xyb[0], xyb[1], xyb[2]);
 }
 
-__global__ void __launch_bounds__(256) k_tables(const ImgDev *imgs, int nimg, int CS, const uint8_t *cand, int E,
-                                                CandEntry *cents, const float4 *labtab /* null unless perceptual */) {
+// A candidate colour component above 32 (possible only in a device-resident list; host lists are refused at the
+// boundary) is clamped to 32 for the tables and raises *fault, which the next snes_ctx_synchronize() reports.
+// Evaluation e = (image e / ncand, candidate e % ncand) takes colour cand[(image * cand_stride + cand_lo + candidate)]:
+// a rank evaluating the slice [cand_lo, cand_lo + ncand) of a list of cand_stride candidates per image reads it in place.
+__global__ void __launch_bounds__(256) k_tables(const ImgDev *imgs, int nimg, int CS, const uint8_t *cand, int E, int ncand,
+                                                int cand_stride, int cand_lo, CandEntry *cents,
+                                                const float4 *labtab /* null unless perceptual */, int *fault) {
     const int tid = threadIdx.x;
     if ((int)blockIdx.x < nimg) {
         const ImgDev im = imgs[blockIdx.x];
@@ -63,10 +69,16 @@ __global__ void __launch_bounds__(256) k_tables(const ImgDev *imgs, int nimg, in
         const int e = ((int)blockIdx.x - nimg) * 256 + tid;
         if (e < E) {
             CandEntry ce;
-            fill_entry(cand[3 * e], cand[3 * e + 1], cand[3 * e + 2], ce.rgb8, ce.lin, ce.xyb);
+            const uint8_t *cp = cand + 3 * ((size_t)(e / ncand) * cand_stride + cand_lo + (e % ncand));
+            uint8_t c5[3] = {cp[0], cp[1], cp[2]};
+            if (c5[0] > 32 || c5[1] > 32 || c5[2] > 32) {
+                atomicOr(fault, 1);
+                for (int c = 0; c < 3; c++) c5[c] = c5[c] > 32 ? 32 : c5[c];
+            }
+            fill_entry(c5[0], c5[1], c5[2], ce.rgb8, ce.lin, ce.xyb);
             ce.lab[0] = ce.lab[1] = ce.lab[2] = 0.0f;
             if (labtab) {
-                const float4 l = labtab[bgr555_index(cand[3 * e], cand[3 * e + 1], cand[3 * e + 2])];
+                const float4 l = labtab[bgr555_index(c5[0], c5[1], c5[2])];
                 ce.lab[0] = l.x;
                 ce.lab[1] = l.y;
                 ce.lab[2] = l.z;
@@ -132,8 +144,10 @@ __global__ void __launch_bounds__(256) k_assign_rgb(const ImgDev *imgs, const Ca
 template <bool SRC>
 __global__ void __launch_bounds__(256) k_pyramid(const ImgDev *imgs, const CandEntry *cents, int ncand, int e0, int S,
                                                  int CS, int ovr, const uint8_t *maps, int from_image,
-                                                 float *xyb_rm_base, float *xyb_cm_base, int lean, int gi_fmt) {
-    // lean != 0 (fused scorer): only the row-major planes of scales >= 1 are written
+                                                 float *xyb_rm_base, int gi_fmt) {
+    // SRC: every scale in both layouts (the column-major copy feeds k_blur_h); candidates: only the row-major planes
+    // of scales >= 1 (the scorer renders scale 0 itself from the palette_map)
+    constexpr bool lean = !SRC;
     __shared__ float s_lin[SRC ? 1 : MAX_ENTRIES + 1][3];
     __shared__ float s_xyb[SRC ? 1 : MAX_ENTRIES + 1][3];
     __shared__ float tile[3][32][33];
@@ -142,7 +156,7 @@ __global__ void __launch_bounds__(256) k_pyramid(const ImgDev *imgs, const CandE
     const int lane = tid & 31, warp = tid >> 5;
     const ImgDev im = imgs[img];
     float *rm = SRC ? const_cast<float *>(im.xyb_rm) : xyb_rm_base + (size_t)e * EVAL_XYB_FLOATS;
-    float *cm = SRC ? const_cast<float *>(im.xyb_cm) : xyb_cm_base + (size_t)e * EVAL_XYB_FLOATS;
+    float *cm = SRC ? const_cast<float *>(im.xyb_cm) : nullptr;
     // from_image: 1 = the image's own palette_map, 2 = its prepared base assignment (gi format, assign_delta.cuh)
     const uint8_t *map = SRC ? nullptr : (from_image == 2 ? im.base_gi : (from_image ? im.map : maps + (size_t)e * NPIX));
     if (!SRC) {
@@ -247,20 +261,20 @@ __global__ void __launch_bounds__(256) k_pyramid(const ImgDev *imgs, const CandE
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_blur_h: horizontal pass of the recursive Gaussian (ssimulacra2 blur, sigma 1.5, radius 5, zero
-// padding) over the planes of one scale.  MODE 0 (candidate): inputs i2 (evaluation) and i1 (image),
-// blurred planes {i2, i2*i2, i1*i2}.  MODE 1 (source): blurred planes {i1, i1*i1}.
-// One lane per image row, walking x = -4 .. d-1 with 3 independent second-order sections per plane:
-//     out_k = n2_k*(in[n-6] + in[n+4]) - prev2_k ; out_k = fma(-d1_k, prev_k, out_k)
-// Inputs come from the column-major copy (consecutive lanes = consecutive rows = consecutive
-// addresses); outputs are transposed through a per-warp shared-memory tile and stored as 128-byte
-// row segments of the row-major H planes  h[e][scale][ch][plane][y][x].
-// grid = ceil(rows / 128), block 128 (4 warps x 32 rows); dynamic smem = 4 * NPL * 32*33 floats.
+// k_blur_h / k_blur_v: the source side of SSIMULACRA2, once per image (the reference recomputes it in every
+// error() call): mu1 = blur(i1) and s11 = blur(i1*i1) for every scale and channel with the recursive Gaussian of
+// ssimulacra2 (sigma 1.5, radius 5, zero padding; 3 second-order sections per plane):
+//   horizontal:  out_k = n2_k*(in[n-6] + in[n+4]) - prev2_k ; out_k = fma(-d1_k, prev_k, out_k)
+//   vertical:    t = fma(prev_k, d1_k, prev2_k) ; out_k = fma(sum, n2_k, -t)
+// k_blur_h: one lane per image row walking x = -4 .. d-1; inputs come from the column-major copy (consecutive lanes
+// = consecutive rows = consecutive addresses), outputs are transposed through a per-warp shared-memory tile and
+// stored as 128-byte row segments of the H planes h[scale][ch][plane][y][x].
+// grid = ceil(rows / 128), block 128 (4 warps x 32 rows); dynamic smem = 4 * 2 * 32*33 floats.
+// k_blur_v: one thread per image column walking y = -4 .. d-1 over the H planes, writes mu1 / s11.
+// grid = ceil(columns / 128), block 128.  (The candidate side of both passes lives in k_score_v3.)
 // ------------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(128) k_blur_h(int s, int nrows_total, const ImgDev *imgs, int ncand, int e0,
-                                                const float *xyb_cm_base, float *h_base) {
-    constexpr int NPL = MODE == 0 ? 3 : 2;
+__global__ void __launch_bounds__(128) k_blur_h(int s, int nrows_total, const ImgDev *imgs, float *h_base) {
+    constexpr int NPL = 2;
     extern __shared__ float smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float(*tile)[32][33] = reinterpret_cast<float(*)[32][33]>(smem + warp * NPL * 32 * 33);
@@ -272,8 +286,7 @@ __global__ void __launch_bounds__(128) k_blur_h(int s, int nrows_total, const Im
     const bool valid = r < nrows_total;
     const int rr = valid ? r : row0;
     const int y = rr % d, ch = (rr / d) % 3, e = rr / (3 * d);
-    const float *in1 = imgs[MODE == 0 ? (e0 + e) / ncand : e].xyb_cm + off3 + (size_t)ch * dd + y;
-    const float *in2 = MODE == 0 ? xyb_cm_base + (size_t)e * EVAL_XYB_FLOATS + off3 + (size_t)ch * dd + y : nullptr;
+    const float *in1 = imgs[e].xyb_cm + off3 + (size_t)ch * dd + y;
     const float n2_0 = c_n2[0], n2_1 = c_n2[1], n2_2 = c_n2[2];
     const float md1_0 = -c_d1[0], md1_1 = -c_d1[1], md1_2 = -c_d1[2];
     float prev[NPL][3], prev2[NPL][3];
@@ -284,24 +297,10 @@ __global__ void __launch_bounds__(128) k_blur_h(int s, int nrows_total, const Im
 
     for (int n = -4; n < d; n++) {
         const int right = n + 4, left = n - 6;
-        float b_r = 0.0f, b_l = 0.0f, a_r = 0.0f, a_l = 0.0f;
-        if (right < d) {
-            b_r = __ldg(in1 + (size_t)right * d);
-            if (MODE == 0) a_r = __ldg(in2 + (size_t)right * d);
-        }
-        if (left >= 0) {
-            b_l = __ldg(in1 + (size_t)left * d);
-            if (MODE == 0) a_l = __ldg(in2 + (size_t)left * d);
-        }
-        float sum[NPL];
-        if (MODE == 0) {
-            sum[0] = a_l + a_r;
-            sum[1] = a_l * a_l + a_r * a_r;
-            sum[2] = b_l * a_l + b_r * a_r;
-        } else {
-            sum[0] = b_l + b_r;
-            sum[1] = b_l * b_l + b_r * b_r;
-        }
+        float b_r = 0.0f, b_l = 0.0f;
+        if (right < d) b_r = __ldg(in1 + (size_t)right * d);
+        if (left >= 0) b_l = __ldg(in1 + (size_t)left * d);
+        const float sum[NPL] = {b_l + b_r, b_l * b_l + b_r * b_r};
 #pragma unroll
         for (int p = 0; p < NPL; p++) {
             float o0 = sum[p] * n2_0 - prev2[p][0];
@@ -336,31 +335,16 @@ __global__ void __launch_bounds__(128) k_blur_h(int s, int nrows_total, const Im
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// k_blur_v: vertical pass of the recursive Gaussian fused with its consumers.  One thread per image
-// column, walking y = -4 .. d-1:   t = fma(prev_k, d1_k, prev2_k) ; out_k = fma(sum, n2_k, -t).
-// MODE 0 (candidate): mu2, s22, s12 are consumed in registers by ssim_map and edge_diff_map of
-//   ssimulacra2 together with the image's precomputed mu1, s11, i1 and the evaluation's i2; the six
-//   f64 sums per (evaluation, scale, channel) are reduced over the warp with a fixed butterfly and
-//   written as per-segment partials (deterministic: no atomics).
-// MODE 1 (source): writes mu1 = blur(i1) and s11 = blur(i1*i1) of the image.
-// grid = ceil(columns / 128), block 128.
-// ------------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(128) k_blur_v(int s, int ncols_total, const ImgDev *imgs, int ncand, int e0,
-                                                const float *xyb_rm_base, const float *h_base, double *partials) {
-    constexpr int NPL = MODE == 0 ? 3 : 2;
+__global__ void __launch_bounds__(128) k_blur_v(int s, int ncols_total, const ImgDev *imgs, const float *h_base) {
+    constexpr int NPL = 2;
     const int d = W >> s, dd = d * d;
     const size_t off3 = 3 * (size_t)scale_off(s);
     const int cidx = blockIdx.x * 128 + threadIdx.x;
-    const bool valid = cidx < ncols_total;
-    const int cc = valid ? cidx : 0;
-    const int x = cc % d, ch = (cc / d) % 3, e = cc / (3 * d);
-    const ImgDev im = imgs[MODE == 0 ? (e0 + e) / ncand : e];
+    if (cidx >= ncols_total) return;
+    const int x = cidx % d, ch = (cidx / d) % 3, e = cidx / (3 * d);
+    const ImgDev im = imgs[e];
     const float *h = h_base + ((size_t)e * 3 * TOTPIX + off3) * NPL + (size_t)(ch * NPL) * dd + x;
     const size_t poff = off3 + (size_t)ch * dd + x;
-    const float *i2p = MODE == 0 ? xyb_rm_base + (size_t)e * EVAL_XYB_FLOATS + poff : nullptr;
-    const float *i1p = im.xyb_rm + poff;
     float *mu1p = im.mu1 + poff, *s11p = im.s11 + poff;
     const float n2_0 = c_n2[0], n2_1 = c_n2[1], n2_2 = c_n2[2];
     const float d1_0 = c_d1[0], d1_1 = c_d1[1], d1_2 = c_d1[2];
@@ -369,128 +353,42 @@ __global__ void __launch_bounds__(128) k_blur_v(int s, int ncols_total, const Im
     for (int p = 0; p < NPL; p++)
 #pragma unroll
         for (int k = 0; k < 3; k++) prev[p][k] = prev2[p][k] = 0.0f;
-    double acc[NSUMS] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-
-    if (valid) {
-        for (int n = -4; n < d; n++) {
-            const int bottom = n + 4, top = n - 6;
-            float val[NPL];
+    for (int n = -4; n < d; n++) {
+        const int bottom = n + 4, top = n - 6;
+        float val[NPL];
 #pragma unroll
-            for (int p = 0; p < NPL; p++) {
-                const float tv = top >= 0 ? __ldg(h + (size_t)p * dd + (size_t)top * d) : 0.0f;
-                const float bv = bottom < d ? __ldg(h + (size_t)p * dd + (size_t)bottom * d) : 0.0f;
-                const float sum = tv + bv;
-                const float t0 = __fmaf_rn(prev[p][0], d1_0, prev2[p][0]);
-                const float t1 = __fmaf_rn(prev[p][1], d1_1, prev2[p][1]);
-                const float t2 = __fmaf_rn(prev[p][2], d1_2, prev2[p][2]);
-                const float o0 = __fmaf_rn(sum, n2_0, -t0);
-                const float o1 = __fmaf_rn(sum, n2_1, -t1);
-                const float o2 = __fmaf_rn(sum, n2_2, -t2);
-                prev2[p][0] = prev[p][0];
-                prev2[p][1] = prev[p][1];
-                prev2[p][2] = prev[p][2];
-                prev[p][0] = o0;
-                prev[p][1] = o1;
-                prev[p][2] = o2;
-                val[p] = (o0 + o1) + o2;
-            }
-            if (n < 0) continue;
-            const size_t ro = (size_t)n * d;
-            if (MODE == 1) {
-                mu1p[ro] = val[0];
-                s11p[ro] = val[1];
-            } else {
-                const float mu2 = val[0], s22 = val[1], s12 = val[2];
-                const float mu1 = __ldg(mu1p + ro), s11 = __ldg(s11p + ro);
-                const float i1 = __ldg(i1p + ro), i2 = __ldg(i2p + ro);
-                // ssim_map
-                const float mu11 = mu1 * mu1, mu22 = mu2 * mu2, mu12 = mu1 * mu2;
-                const float mu_diff = mu1 - mu2;
-                const float num_m = __fmaf_rn(mu_diff, -mu_diff, 1.0f);
-                const float num_s = __fmaf_rn(2.0f, s12 - mu12, 0.0009f);
-                const float denom_s = (s11 - mu11) + (s22 - mu22) + 0.0009f;
-                double dv = 1.0 - (double)((num_m * num_s) / denom_s);
-                dv = fmax(dv, 0.0);
-                acc[0] += dv;
-                const double dv2 = dv * dv;
-                acc[1] += dv2 * dv2;
-                // edge_diff_map
-                const double d1v = (1.0 + (double)fabsf(i2 - mu2)) / (1.0 + (double)fabsf(i1 - mu1)) - 1.0;
-                const double art = fmax(d1v, 0.0);
-                acc[2] += art;
-                const double art2 = art * art;
-                acc[3] += art2 * art2;
-                const double det = fmax(-d1v, 0.0);
-                acc[4] += det;
-                const double det2 = det * det;
-                acc[5] += det2 * det2;
-            }
+        for (int p = 0; p < NPL; p++) {
+            const float tv = top >= 0 ? __ldg(h + (size_t)p * dd + (size_t)top * d) : 0.0f;
+            const float bv = bottom < d ? __ldg(h + (size_t)p * dd + (size_t)bottom * d) : 0.0f;
+            const float sum = tv + bv;
+            const float t0 = __fmaf_rn(prev[p][0], d1_0, prev2[p][0]);
+            const float t1 = __fmaf_rn(prev[p][1], d1_1, prev2[p][1]);
+            const float t2 = __fmaf_rn(prev[p][2], d1_2, prev2[p][2]);
+            const float o0 = __fmaf_rn(sum, n2_0, -t0);
+            const float o1 = __fmaf_rn(sum, n2_1, -t1);
+            const float o2 = __fmaf_rn(sum, n2_2, -t2);
+            prev2[p][0] = prev[p][0];
+            prev2[p][1] = prev[p][1];
+            prev2[p][2] = prev[p][2];
+            prev[p][0] = o0;
+            prev[p][1] = o1;
+            prev[p][2] = o2;
+            val[p] = (o0 + o1) + o2;
         }
-    }
-    if (MODE == 0) {
-        const int segw = d < 32 ? d : 32;
-#pragma unroll
-        for (int q = 0; q < NSUMS; q++) {
-            double v = acc[q];
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) {
-                const double other = __shfl_xor_sync(0xffffffffu, v, o);
-                if (o < segw) v += other;
-            }
-            acc[q] = v;
-        }
-        if (valid && (threadIdx.x & (segw - 1)) == 0) {
-            const int seg = d >= 32 ? x >> 5 : 0;
-            double *out = partials + (size_t)(e0 + e) * PART_DOUBLES + (((size_t)s * 3 + ch) * NSEG + seg) * NSUMS;
-#pragma unroll
-            for (int q = 0; q < NSUMS; q++) out[q] = acc[q];
-        }
+        if (n < 0) continue;
+        mu1p[(size_t)n * d] = val[0];
+        s11p[(size_t)n * d] = val[1];
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// k_pool: Msssim::score of ssimulacra2 (108-weight pooling, cubic, power) and error() = 100 - score
-// (lib.rs:547).  One thread per evaluation; partial sums are added in a fixed order.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_pool(const double *partials, int E, double *scores) {
-    const int e = blockIdx.x * 128 + threadIdx.x;
-    if (e >= E) return;
-    const double *pe = partials + (size_t)e * PART_DOUBLES;
-    double ssim = 0.0;
-    int i = 0;
-    for (int c = 0; c < 3; c++)
-        for (int s = 0; s < NSCALES; s++) {
-            const int d = W >> s;
-            const int nseg = d >= 32 ? d / 32 : 1;
-            const double opp = 1.0 / (double)(d * d);
-            double sum[NSUMS] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-            for (int g = 0; g < nseg; g++)
-                for (int q = 0; q < NSUMS; q++) sum[q] += pe[(((size_t)s * 3 + c) * NSEG + g) * NSUMS + q];
-            const double ssim0 = opp * sum[0], ssim1 = sqrt(sqrt(opp * sum[1]));
-            const double e0 = opp * sum[2], e1 = sqrt(sqrt(opp * sum[3]));
-            const double e2 = opp * sum[4], e3 = sqrt(sqrt(opp * sum[5]));
-            ssim = fma(c_weight[i++], fabs(ssim0), ssim);
-            ssim = fma(c_weight[i++], fabs(e0), ssim);
-            ssim = fma(c_weight[i++], fabs(e2), ssim);
-            ssim = fma(c_weight[i++], fabs(ssim1), ssim);
-            ssim = fma(c_weight[i++], fabs(e1), ssim);
-            ssim = fma(c_weight[i++], fabs(e3), ssim);
-        }
-    ssim *= 0.9562382616834844;
-    ssim = fma(6.248496625763138e-5 * ssim * ssim, ssim, fma(2.326765642916932, ssim, -0.020884521182843837 * ssim * ssim));
-    double score = 100.0;
-    if (ssim > 0.0) score = fma(pow(ssim, 0.6276336467831387), -10.0, 100.0);
-    scores[e] = 100.0 - score;
+__device__ __forceinline__ bool best_less(double ea, int ia, double eb, int ib) {
+    return ea < eb || (ea == eb && ia < ib);
 }
 
 // ------------------------------------------------------------------------------------------------
 // k_argmin: per image, strict-< first minimum over its candidates' errors (lib.rs:216, 258, 302),
 // i.e. the lexicographic minimum of (error, candidate index).  grid = nimg, block 128.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool best_less(double ea, int ia, double eb, int ib) {
-    return ea < eb || (ea == eb && ia < ib);
-}
-
 __global__ void __launch_bounds__(128) k_argmin(const double *scores, int ncand, int idx_base, Best *best) {
     __shared__ double s_e[4];
     __shared__ int s_i[4];
@@ -532,15 +430,26 @@ __global__ void __launch_bounds__(128) k_argmin(const double *scores, int ncand,
     }
 }
 
+// "no candidate was evaluated" records (a rank whose candidate slice is empty)
+__global__ void k_no_best(Best *best, int nimg) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nimg) return;
+    Best b;
+    b.err = __longlong_as_double(0x7ff0000000000000ll);
+    b.idx = -1;
+    b.pad = 0;
+    best[j] = b;
+}
+
 // k_merge_best: the cross-rank argmin after the all-gather: gathered[r][j] is rank r's (error, index)
 // for image j, with indices already global; the lexicographic minimum reproduces the strict-< /
 // lowest-index-wins rule of lib.rs:216 for any number of ranks.  One thread per image.
-__global__ void k_merge_best(const Best *gathered, int nranks, int nimg, Best *out) {
+__global__ void k_merge_best(const Best *gathered, int nranks, int rank_stride /* records per rank, >= nimg */, int nimg, Best *out) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nimg) return;
     Best b = gathered[j];
     for (int r = 1; r < nranks; r++) {
-        const Best o = gathered[(size_t)r * nimg + j];
+        const Best o = gathered[(size_t)r * rank_stride + j];
         if (o.idx >= 0 && (b.idx < 0 || best_less(o.err, o.idx, b.err, b.idx))) b = o;
     }
     out[j] = b;
@@ -558,8 +467,9 @@ __global__ void k_apply_best(const ImgDev *imgs, int nimg, int slot, const uint8
     const Best b = best[j];
     if (b.idx < 0 || b.idx >= ncand_all) return;
     const ImgDev im = imgs[j];
+    const uint8_t *c = cand_all + ((size_t)j * ncand_all + b.idx) * 3;
+    if (c[0] > 32 || c[1] > 32 || c[2] > 32) return;   // never a SnesColor (flagged by k_tables): not applied
     if (force || b.err < *im.cur_err) {
-        const uint8_t *c = cand_all + ((size_t)j * ncand_all + b.idx) * 3;
         im.palette[3 * slot] = c[0];
         im.palette[3 * slot + 1] = c[1];
         im.palette[3 * slot + 2] = c[2];

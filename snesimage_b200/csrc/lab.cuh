@@ -128,11 +128,12 @@ __device__ inline float ciede2000(float l1, float a1, float b1, float l2, float 
 }
 
 // SnesColor 5-bit value -> index into the BGR555 table.  round(v/8) can store 32 (lib.rs:396-400),
-// whose as_rgba() wraps to 8 == as_rgba(1) (lib.rs:664); callers guarantee v <= 32.
+// whose as_rgba() wraps to 8 == as_rgba(1) (lib.rs:664).  Values above 32 are refused at the boundary (host lists) or
+// flagged by k_tables (device lists); the mask keeps the table lookup in range whatever arrives.
 __device__ __forceinline__ int bgr555_index(int r5, int g5, int b5) {
-    r5 = r5 == 32 ? 1 : r5;
-    g5 = g5 == 32 ? 1 : g5;
-    b5 = b5 == 32 ? 1 : b5;
+    r5 = r5 == 32 ? 1 : (r5 & 31);
+    g5 = g5 == 32 ? 1 : (g5 & 31);
+    b5 = b5 == 32 ? 1 : (b5 & 31);
     return r5 | (g5 << 5) | (b5 << 10);  // SnesColor::as_u16, lib.rs:679-681
 }
 

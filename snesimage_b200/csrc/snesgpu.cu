@@ -17,7 +17,6 @@
 #include "kernels.cuh"
 #include "kmeans.cuh"
 #include "lab.cuh"
-#include "score_fused.cuh"
 #include "score_v2.cuh"
 #include "score_v3.cuh"
 #include "assign_delta.cuh"
@@ -57,18 +56,19 @@ struct snes_ctx {
     cudaStream_t own = nullptr, stream = nullptr;
     int64_t launches = 0;
     int chunk = 2048;  // evaluations whose scratch (palette_map, coarse XYB pyramid) is live at once
-    int fused = 3;    // 3: k_score_v3 (persistent 4-warp CTAs); 2: k_score_v2; 1: k_score_fused; 0: multi-kernel pipeline (SNESGPU_FUSED)
+    int fused = 3;    // 3: k_score_v3 (persistent 4-warp CTAs); 2: k_score_v2, its predecessor, kept as the A/B check (SNESGPU_FUSED)
     int nsm = 148;
     int *v3_counter = nullptr;
     float *v3_scratch = nullptr;
     float *self_xyb = nullptr;        // [img_cap][EVAL_XYB_FLOATS] coarse pyramid of the images' own state (fused error + candidates)
     double *self_partials = nullptr;  // [img_cap][NSCALES*3*NSUMS]
-    int bw = 32;      // column-block width of the fused scorer (16 or 32, SNESGPU_BW)
     int delta = 1;    // 1: no-dither candidates re-decide only the pixels the replaced entry can change (SNESGPU_DELTA)
 
     // per-chunk scratch
-    size_t chunk_cap = 0, pipe_cap = 0;
-    float *xyb_rm = nullptr, *xyb_cm = nullptr, *hbuf = nullptr;
+    size_t chunk_cap = 0;
+    float *xyb_rm = nullptr;
+    float *hbuf = nullptr;   // H planes of one image's source-side blur (image creation); also the as_rgba staging buffer
+    int *d_fault = nullptr;  // set by k_tables when a device-resident candidate list holds a colour component > 32
     uint8_t *maps = nullptr;
     // per-batch scratch
     size_t eval_cap = 0;
@@ -82,6 +82,8 @@ struct snes_ctx {
     Best *best = nullptr;
     double *self_scores = nullptr;
     std::vector<snes_image *> cached;
+
+    int shard_ncand_all = 0;   // candidates per image of the list snes_batch_step_random_shard_begin left in `cand`
 
     float4 *labtab = nullptr;  // BGR555 -> Lab<D65,f32>
 
@@ -274,8 +276,9 @@ static const uint8_t kNes[NES_COUNT][3] = {  // lib.rs:687-742
     {8, 24, 24},  {9, 9, 9},    {31, 31, 31}, {25, 29, 31}, {27, 27, 31}, {29, 27, 31}, {31, 26, 31}, {31, 26, 30},
     {31, 27, 25}, {31, 28, 22}, {30, 30, 21}, {27, 31, 21}, {25, 31, 23}, {24, 31, 26}, {24, 30, 30}, {23, 24, 23}};
 
-static constexpr int kBlurHSmem0 = 4 * 3 * 32 * 33 * (int)sizeof(float);
-static constexpr int kBlurHSmem1 = 4 * 2 * 32 * 33 * (int)sizeof(float);
+static constexpr int kBlurHSmem = 4 * 2 * 32 * 33 * (int)sizeof(float);
+
+static int ctx_init(snes_ctx *ctx, int nsm);
 
 extern "C" int snes_ctx_create(int device, snes_ctx **out) {
     if (!out) return fail(SNES_E_INVALID, "snes_ctx_create: out is NULL");
@@ -289,6 +292,18 @@ extern "C" int snes_ctx_create(int device, snes_ctx **out) {
         return fail(SNES_E_CUDA, std::string("snes_ctx_create: libsnesgpu is built for sm_100a only; device is ") + prop.name);
     snes_ctx *ctx = new snes_ctx();
     ctx->device = device;
+    const int rc = ctx_init(ctx, prop.multiProcessorCount);
+    if (rc != SNES_OK) {   // g_err holds the message of the step that failed
+        const std::string msg = g_err;
+        snes_ctx_destroy(ctx);
+        return fail(rc, msg);
+    }
+    *out = ctx;
+    return SNES_OK;
+}
+
+static int ctx_init(snes_ctx *ctx, int nsm) {
+    const int device = ctx->device;
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&ctx->own, cudaStreamNonBlocking));
     ctx->stream = ctx->own;
@@ -297,8 +312,7 @@ extern "C" int snes_ctx_create(int device, snes_ctx **out) {
         if (v > 0) ctx->chunk = v;
     }
 
-    if (const char *c = getenv("SNESGPU_FUSED")) ctx->fused = atoi(c) < 0 ? 0 : (atoi(c) > 3 ? 3 : atoi(c));
-    if (const char *c = getenv("SNESGPU_BW")) ctx->bw = atoi(c) == 16 ? 16 : 32;
+    if (const char *c = getenv("SNESGPU_FUSED")) ctx->fused = atoi(c) == 2 ? 2 : 3;
     if (const char *c = getenv("SNESGPU_DELTA")) ctx->delta = atoi(c) != 0;
 
     float lut[256], lut2[256], n2[3], d1[3];
@@ -337,28 +351,25 @@ extern "C" int snes_ctx_create(int device, snes_ctx **out) {
     }
     CK(cudaMemcpyToSymbol(c_weight, kWeights, sizeof(kWeights)));
     CK(cudaMemcpyToSymbol(c_nes, nes4, sizeof(nes4)));
-    CK(cudaFuncSetAttribute(k_blur_h<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlurHSmem0));
-    CK(cudaFuncSetAttribute(k_blur_h<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlurHSmem1));
-    CK(cudaFuncSetAttribute(k_score_fused<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<32>)));
-    CK(cudaFuncSetAttribute(k_score_fused<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<16>)));
+    CK(cudaFuncSetAttribute(k_blur_h, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlurHSmem));
     CK(cudaFuncSetAttribute(k_score_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V2Smem)));
     CK(cudaFuncSetAttribute(k_score_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V3Smem)));
     CK(cudaFuncSetAttribute(k_score_v3, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    ctx->nsm = prop.multiProcessorCount;
+    ctx->nsm = nsm;
     RET(dev_alloc(&ctx->v3_counter, 1));
+    RET(dev_alloc(&ctx->hbuf, (size_t)EVAL_XYB_FLOATS * 2));
+    RET(dev_alloc(&ctx->d_fault, 1));
+    CK(cudaMemsetAsync(ctx->d_fault, 0, sizeof(int), ctx->stream));
     RET(dev_alloc(&ctx->v3_scratch, (size_t)ctx->nsm * V3_CTAS_PER_SM * V3_HSCRATCH_FLOATS));
 
     RET(dev_alloc(&ctx->labtab, 32768));
     LAUNCH(ctx, "k_build_lab_table", k_build_lab_table<<<128, 256, 0, ctx->stream>>>(ctx->labtab));
     CK(cudaStreamSynchronize(ctx->stream));
-    *out = ctx;
     return SNES_OK;
 }
 
 static void free_scratch(snes_ctx *ctx) {
     cudaFree(ctx->xyb_rm);
-    cudaFree(ctx->xyb_cm);
-    cudaFree(ctx->hbuf);
     cudaFree(ctx->maps);
     cudaFree(ctx->partials);
     cudaFree(ctx->scores);
@@ -377,13 +388,15 @@ static void free_scratch(snes_ctx *ctx) {
 extern "C" void snes_ctx_destroy(snes_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_scratch(ctx);
     cudaFree(ctx->labtab);
+    cudaFree(ctx->hbuf);
+    cudaFree(ctx->d_fault);
     cudaFree(ctx->v3_counter);
     cudaFree(ctx->v3_scratch);
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
-    cudaStreamDestroy(ctx->own);
+    if (ctx->own) cudaStreamDestroy(ctx->own);
     delete ctx;
 }
 
@@ -400,7 +413,13 @@ extern "C" int snes_ctx_set_stream(snes_ctx *ctx, void *cuda_stream) {
 extern "C" int snes_ctx_synchronize(snes_ctx *ctx) {
     if (!ctx) return fail(SNES_E_INVALID, "ctx is NULL");
     RET(set_device(ctx));
+    int fault = 0;
+    CK(cudaMemcpyAsync(&fault, ctx->d_fault, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (fault) {
+        CK(cudaMemsetAsync(ctx->d_fault, 0, sizeof(int), ctx->stream));
+        return fail(SNES_E_INVALID, "a device-resident candidate list held a colour component > 32 (clamped for evaluation, never applied)");
+    }
     return SNES_OK;
 }
 
@@ -453,9 +472,9 @@ extern "C" int snes_ctx_profile_end(snes_ctx *ctx, char *buf, size_t cap, size_t
 }
 
 extern "C" int snes_ctx_set_scorer(snes_ctx *ctx, int fused, int block_width, int delta_assign) {
-    if (!ctx || (block_width != 16 && block_width != 32)) return fail(SNES_E_INVALID, "snes_ctx_set_scorer: bad argument");
-    ctx->fused = fused < 0 ? 0 : (fused > 3 ? 3 : fused);
-    ctx->bw = block_width;
+    (void)block_width;   // the column block is fixed at 32 since k_score_fused<16/32> left the build
+    if (!ctx || (fused != 2 && fused != 3)) return fail(SNES_E_INVALID, "snes_ctx_set_scorer: scorer must be 3 (k_score_v3) or 2 (k_score_v2)");
+    ctx->fused = fused;
     ctx->delta = delta_assign != 0;
     return SNES_OK;
 }
@@ -467,9 +486,8 @@ extern "C" int snes_ctx_set_chunk(snes_ctx *ctx, int evaluations) {
 }
 
 // ---- scratch management ------------------------------------------------------------------------
-// Scratch of one chunk of evaluations.  The fused path needs only the palette_map (64 KiB) and the coarse XYB
-// pyramid per evaluation; the column-major copy and the H planes exist for the multi-kernel pipeline only.
-static int ensure_chunk(snes_ctx *ctx, size_t n, bool pipeline) {
+// Scratch of one chunk of evaluations: the palette_map (64 KiB) and the coarse XYB pyramid per evaluation.
+static int ensure_chunk(snes_ctx *ctx, size_t n) {
     if (n > ctx->chunk_cap) {
         CK(cudaStreamSynchronize(ctx->stream));
         cudaFree(ctx->xyb_rm);
@@ -480,16 +498,6 @@ static int ensure_chunk(snes_ctx *ctx, size_t n, bool pipeline) {
         RET(dev_alloc(&ctx->xyb_rm, n * EVAL_XYB_FLOATS));
         RET(dev_alloc(&ctx->maps, n * NPIX));
         ctx->chunk_cap = n;
-    }
-    if (pipeline && n > ctx->pipe_cap) {
-        CK(cudaStreamSynchronize(ctx->stream));
-        cudaFree(ctx->xyb_cm);
-        cudaFree(ctx->hbuf);
-        ctx->xyb_cm = ctx->hbuf = nullptr;
-        ctx->pipe_cap = 0;
-        RET(dev_alloc(&ctx->xyb_cm, n * EVAL_XYB_FLOATS));
-        RET(dev_alloc(&ctx->hbuf, n * EVAL_XYB_FLOATS * 3));
-        ctx->pipe_cap = n;
     }
     return SNES_OK;
 }
@@ -538,7 +546,7 @@ static int ensure_imgs(snes_ctx *ctx, size_t n) {
     RET(dev_alloc(&ctx->best, n));
     RET(dev_alloc(&ctx->self_scores, n));
     RET(dev_alloc(&ctx->self_xyb, 2 * n * EVAL_XYB_FLOATS));  // [0, n): own palette_map; [n, 2n): prepared base assignment
-    RET(dev_alloc(&ctx->self_partials, n * NSCALES * 3 * NSUMS));
+    RET(dev_alloc(&ctx->self_partials, n * PART_DOUBLES));
     ctx->img_cap = n;
     return SNES_OK;
 }
@@ -573,7 +581,8 @@ struct EvalPlan {
     int nimg = 0;
     int ncand = 1;                    // evaluations per image
     int ovr = -1;                     // palette slot replaced by the candidate colour, -1: none
-    const uint8_t *d_cand = nullptr;  // [nimg*ncand][3] device, required when ovr >= 0
+    const uint8_t *d_cand = nullptr;  // device, required when ovr >= 0: [nimg][cand_stride][3], evaluation (j, k) reads candidate cand_lo + k
+    int cand_stride = 0, cand_lo = 0; // candidates per image in d_cand (0: ncand) and the first one this plan evaluates
     bool self = false;                // operate on the images' own palette_map instead of scratch maps
     bool do_assign = false;           // optimize()
     bool do_score = false;            // error()
@@ -602,12 +611,8 @@ static int launch_scorer(snes_ctx *ctx, const FusedArgs &fa, int ec, const Fused
         const int grid = items < ctx->nsm * V3_CTAS_PER_SM ? items : ctx->nsm * V3_CTAS_PER_SM;
         CK(cudaMemsetAsync(ctx->v3_counter, 0, sizeof(int), st));
         LAUNCH(ctx, "k_score_v3", k_score_v3<<<grid, V3_THREADS, sizeof(V3Smem), st>>>(va));
-    } else if (ctx->fused == 2)
+    } else
         LAUNCH(ctx, "k_score_v2", k_score_v2<<<dim3(3, ec), V2_THREADS, sizeof(V2Smem), st>>>(fa));
-    else if (ctx->bw == 16)
-        LAUNCH(ctx, "k_score_fused<16>", k_score_fused<16><<<dim3(3, ec), FUSED_THREADS, sizeof(FusedSmem<16>), st>>>(fa));
-    else
-        LAUNCH(ctx, "k_score_fused<32>", k_score_fused<32><<<dim3(3, ec), FUSED_THREADS, sizeof(FusedSmem<32>), st>>>(fa));
     return SNES_OK;
 }
 
@@ -617,21 +622,22 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
     cudaStream_t st = ctx->stream;
     RET(ensure_evals(ctx, (size_t)E));
     const int chunk = E < ctx->chunk ? E : ctx->chunk;
-    if (pl.do_score || (pl.do_assign && !pl.self && !pl.d_maps_out)) RET(ensure_chunk(ctx, (size_t)chunk, !ctx->fused));
+    if (pl.do_score || (pl.do_assign && !pl.self && !pl.d_maps_out)) RET(ensure_chunk(ctx, (size_t)chunk));
     const float4 *labtab = cfg.perceptual_palettes ? ctx->labtab : nullptr;
 
     LAUNCH(ctx, "k_tables", k_tables<<<pl.nimg + (pl.ovr >= 0 ? (E + 255) / 256 : 0), 256, 0, st>>>(ctx->d_imgs, pl.nimg, CS, pl.d_cand,
-                                                                          pl.ovr >= 0 ? E : 0, ctx->cents, labtab));
+                                                                          pl.ovr >= 0 ? E : 0, pl.ncand, pl.cand_stride ? pl.cand_stride : pl.ncand,
+                                                                          pl.cand_lo, ctx->cents, labtab, ctx->d_fault));
 
     // error() of the images' own state riding in the candidates' scorer launch: its coarse pyramid and partial sums
     // live in their own buffers; the 3 * nimg extra items join the first chunk
     const bool self_too = pl.with_self_error && ctx->fused == 3 && pl.do_score && !pl.self;
-    const bool delta_path = ctx->fused && ctx->delta && !cfg.dither && pl.do_assign && pl.do_score && !pl.self && !pl.d_maps_out &&
+    const bool delta_path = ctx->delta && !cfg.dither && pl.do_assign && pl.do_score && !pl.self && !pl.d_maps_out &&
                             pl.ovr >= 0 && CS <= 255;
     FusedArgs fself;
     if (self_too) {  // the coarse pyramid of the images' own palette_map: input of their error()
         LAUNCH(ctx, "k_pyramid<false>", k_pyramid<false><<<dim3(16, pl.nimg), 256, 0, st>>>(ctx->d_imgs, ctx->cents, 1, 0, S, CS, -1, nullptr, 1,
-                                                       ctx->self_xyb, nullptr, 1, 0));
+                                                       ctx->self_xyb, 0));
         fself.imgs = ctx->d_imgs;
         fself.cents = ctx->cents;
         fself.ncand = 1;
@@ -656,7 +662,7 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
         // coarse pyramid of the prepared base assignment (current palette, no candidate): k_assign_pyr copies the blocks
         // a candidate leaves unchanged from it
         LAUNCH(ctx, "k_pyramid<false>", k_pyramid<false><<<dim3(16, pl.nimg), 256, 0, st>>>(ctx->d_imgs, ctx->cents, 1, 0, S, CS, -1, nullptr, 2,
-                                                       ctx->self_xyb + (size_t)ctx->img_cap * EVAL_XYB_FLOATS, nullptr, 1, 1));
+                                                       ctx->self_xyb + (size_t)ctx->img_cap * EVAL_XYB_FLOATS, 1));
     }
 
     for (int e0 = 0; e0 < E; e0 += chunk) {
@@ -684,7 +690,7 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
             continue;
         }
         // scratch maps feed only the fused scorer: write global entry indices (no tile_palettes / alpha lookups later)
-        int gi = (ctx->fused && pl.do_score && !pl.self && !pl.d_maps_out && CS <= 255) ? 1 : 0;
+        int gi = (pl.do_score && !pl.self && !pl.d_maps_out && CS <= 255) ? 1 : 0;
         if (pl.d_moves && pl.do_score) {
             // a tile move changes the tile's subpalette for this evaluation only, so the scorer must not look it up in
             // the image: score from a gi-format scratch map; a palette_map-format copy for the caller is a second pass
@@ -714,46 +720,31 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
             }
         }
         if (!pl.do_score) continue;
-        if (ctx->fused) {
-            if (gi)
-                LAUNCH(ctx, "k_assign_pyr<2>", k_assign_pyr<2><<<dim3(4, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, ctx->xyb_rm, nullptr));
-            else
-                LAUNCH(ctx, "k_pyramid<false>", k_pyramid<false><<<dim3(16, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self,
-                                                       ctx->xyb_rm, ctx->xyb_cm, 1, gi));
-            FusedArgs fa;
-            fa.imgs = ctx->d_imgs;
-            fa.cents = ctx->cents;
-            fa.ncand = pl.ncand;
-            fa.e0 = e0;
-            fa.S = S;
-            fa.CS = CS;
-            fa.ovr = pl.ovr;
-            fa.maps = maps;
-            fa.from_image = pl.self;
-            fa.gi_fmt = gi;
-            fa.xyb_rm = ctx->xyb_rm;
-            fa.partials = ctx->partials;
-            RET(launch_scorer(ctx, fa, ec, (self_too && e0 == 0) ? &fself : nullptr, pl.nimg));
-            continue;
-        }
-        LAUNCH(ctx, "k_pyramid<false>", k_pyramid<false><<<dim3(16, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self,
-                                                       ctx->xyb_rm, ctx->xyb_cm, 0, 0));
-        for (int s = 0; s < NSCALES; s++) {
-            const int d = W >> s, lines = ec * 3 * d;
-            LAUNCH(ctx, "k_blur_h<0>", k_blur_h<0><<<(lines + 127) / 128, 128, kBlurHSmem0, st>>>(s, lines, ctx->d_imgs, pl.ncand, e0, ctx->xyb_cm, ctx->hbuf));
-            LAUNCH(ctx, "k_blur_v<0>", k_blur_v<0><<<(lines + 127) / 128, 128, 0, st>>>(s, lines, ctx->d_imgs, pl.ncand, e0, ctx->xyb_rm, ctx->hbuf,
-                                                           ctx->partials));
-        }
+        if (gi)
+            LAUNCH(ctx, "k_assign_pyr<2>", k_assign_pyr<2><<<dim3(4, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, ctx->xyb_rm, nullptr));
+        else
+            LAUNCH(ctx, "k_pyramid<false>", k_pyramid<false><<<dim3(16, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self,
+                                                   ctx->xyb_rm, gi));
+        FusedArgs fa;
+        fa.imgs = ctx->d_imgs;
+        fa.cents = ctx->cents;
+        fa.ncand = pl.ncand;
+        fa.e0 = e0;
+        fa.S = S;
+        fa.CS = CS;
+        fa.ovr = pl.ovr;
+        fa.maps = maps;
+        fa.from_image = pl.self;
+        fa.gi_fmt = gi;
+        fa.xyb_rm = ctx->xyb_rm;
+        fa.partials = ctx->partials;
+        RET(launch_scorer(ctx, fa, ec, (self_too && e0 == 0) ? &fself : nullptr, pl.nimg));
     }
     if (self_too) {
         LAUNCH(ctx, "k_pool_fused", k_pool_fused<<<(pl.nimg + 127) / 128, 128, 0, st>>>(ctx->self_partials, pl.nimg, ctx->self_scores));
         LAUNCH(ctx, "k_store_cur_err", k_store_cur_err<<<(pl.nimg + 127) / 128, 128, 0, st>>>(ctx->d_imgs, pl.nimg, ctx->self_scores));
     }
-    if (pl.do_score && ctx->fused) {
-        LAUNCH(ctx, "k_pool_fused", k_pool_fused<<<(E + 127) / 128, 128, 0, st>>>(ctx->partials, E, pl.d_scores));
-    } else if (pl.do_score) {
-        LAUNCH(ctx, "k_pool", k_pool<<<(E + 127) / 128, 128, 0, st>>>(ctx->partials, E, pl.d_scores));
-    }
+    if (pl.do_score) LAUNCH(ctx, "k_pool_fused", k_pool_fused<<<(E + 127) / 128, 128, 0, st>>>(ctx->partials, E, pl.d_scores));
     return SNES_OK;
 }
 
@@ -856,12 +847,11 @@ extern "C" int snes_image_new(snes_ctx *ctx, const uint8_t *rgba, int width, int
         // source side of SSIMULACRA2, once per image: XYB pyramid, mu1 = blur(i1), s11 = blur(i1*i1)
         snes_image *one[1] = {im};
         RET(bind_images(ctx, one, 1));
-        RET(ensure_chunk(ctx, 1, true));
-        LAUNCH(ctx, "k_pyramid<true>", k_pyramid<true><<<dim3(16, 1), 256, 0, st>>>(ctx->d_imgs, nullptr, 1, 0, 0, 0, -1, nullptr, 0, nullptr, nullptr, 0, 0));
+        LAUNCH(ctx, "k_pyramid<true>", k_pyramid<true><<<dim3(16, 1), 256, 0, st>>>(ctx->d_imgs, nullptr, 1, 0, 0, 0, -1, nullptr, 0, nullptr, 0));
         for (int s = 0; s < NSCALES; s++) {
             const int d = W >> s, lines = 3 * d;
-            LAUNCH(ctx, "k_blur_h<1>", k_blur_h<1><<<(lines + 127) / 128, 128, kBlurHSmem1, st>>>(s, lines, ctx->d_imgs, 1, 0, nullptr, ctx->hbuf));
-            LAUNCH(ctx, "k_blur_v<1>", k_blur_v<1><<<(lines + 127) / 128, 128, 0, st>>>(s, lines, ctx->d_imgs, 1, 0, nullptr, ctx->hbuf, nullptr));
+            LAUNCH(ctx, "k_blur_h", k_blur_h<<<(lines + 127) / 128, 128, kBlurHSmem, st>>>(s, lines, ctx->d_imgs, ctx->hbuf));
+            LAUNCH(ctx, "k_blur_v", k_blur_v<<<(lines + 127) / 128, 128, 0, st>>>(s, lines, ctx->d_imgs, ctx->hbuf));
         }
         LAUNCH(ctx, "k_interleave_ms", k_interleave_ms<<<(EVAL_XYB_FLOATS + 255) / 256, 256, 0, st>>>(im->dev.mu1, im->dev.s11, im->dev.ms11, EVAL_XYB_FLOATS));
         CK(cudaStreamSynchronize(st));
@@ -934,13 +924,12 @@ static int batch_recalc(snes_ctx *ctx, snes_image *const *images, int nimg, int 
     // grid is (image, subpalette) with C as the stride; with only_sub0 the grid covers subpalette 0 only
     LAUNCH(ctx, "k_kmeans<false>", k_kmeans<false><<<nimg * C, 1024, 0, st>>>(ctx->d_imgs, ctx->d_km, C, S));
     LAUNCH(ctx, "k_centres_to_palette", k_centres_to_palette<<<nimg, 256, 0, st>>>(ctx->d_imgs, ctx->d_km, C, S, cfg.perceptual_palettes, cfg.nes, ctx->labtab, 0));
-    std::vector<int> status(C);
-    for (int j = 0; j < nimg; j++) {
-        CK(cudaMemcpyAsync(status.data(), images[j]->km.status, sizeof(int) * C, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        for (int p = 0; p < C; p++)
-            if (status[p] != 0) return fail(SNES_E_KMEANS, "cogset Kmeans::new: assertion failed: 2 <= k && k < data.len()");
-    }
+    std::vector<int> status((size_t)nimg * C);
+    for (int j = 0; j < nimg; j++)
+        CK(cudaMemcpyAsync(status.data() + (size_t)j * C, images[j]->km.status, sizeof(int) * C, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int v : status)
+        if (v != 0) return fail(SNES_E_KMEANS, "cogset Kmeans::new: assertion failed: 2 <= k && k < data.len()");
     return SNES_OK;
 }
 
@@ -966,12 +955,11 @@ extern "C" int snes_batch_initialize_tiles(snes_ctx *ctx, snes_image *const *ima
         LAUNCH(ctx, "k_kmeans<true>", k_kmeans<true><<<nimg, 1024, 0, st>>>(ctx->d_imgs, ctx->d_km, cfg.subpalette_count, cfg.subpalette_count));
         LAUNCH(ctx, "k_centres_to_palette", k_centres_to_palette<<<nimg, 256, 0, st>>>(ctx->d_imgs, ctx->d_km, cfg.subpalette_count, cfg.subpalette_size,
                                                   cfg.perceptual_palettes, cfg.nes, ctx->labtab, 1));
-        for (int j = 0; j < nimg; j++) {
-            int status = -1;
-            CK(cudaMemcpyAsync(&status, images[j]->km.status, sizeof(int), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            if (status != 0) return fail(SNES_E_KMEANS, "cogset Kmeans::new: assertion failed: 2 <= k && k < data.len()");
-        }
+        std::vector<int> status(nimg, -1);
+        for (int j = 0; j < nimg; j++) CK(cudaMemcpyAsync(&status[j], images[j]->km.status, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int v : status)
+            if (v != 0) return fail(SNES_E_KMEANS, "cogset Kmeans::new: assertion failed: 2 <= k && k < data.len()");
     }
     RET(batch_optimize(ctx, images, nimg));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1025,7 +1013,6 @@ extern "C" int snes_image_as_rgba(snes_image *im, uint8_t *out_rgba) {
     if (!im || !out_rgba) return fail(SNES_E_INVALID, "snes_image_as_rgba: NULL argument");
     snes_ctx *ctx = im->ctx;
     RET(set_device(ctx));
-    RET(ensure_chunk(ctx, 1, true));
     uchar4 *tmp = reinterpret_cast<uchar4 *>(ctx->hbuf);
     LAUNCH(ctx, "k_as_rgba", k_as_rgba<<<256, 256, 0, ctx->stream>>>(im->dev, im->cfg.subpalette_size, tmp));
     CK(cudaMemcpyAsync(out_rgba, tmp, NPIX * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1073,6 +1060,23 @@ extern "C" int snes_image_set_palette_map(snes_image *im, const uint8_t *in) {
     for (int i = 0; i < NPIX; i++)
         if (in[i] >= im->cfg.subpalette_size) return fail(SNES_E_INVALID, "snes_image_set_palette_map: index >= subpalette_size");
     return h2d(im, im->dev.map, in, NPIX);
+}
+
+// FNV-1a (64-bit) over palette, tile_palettes and palette_map: what replicas of an image on different ranks must agree on.
+extern "C" int snes_image_state_checksum(snes_image *im, uint64_t *out) {
+    if (!im || !out) return fail(SNES_E_INVALID, "snes_image_state_checksum: NULL argument");
+    const size_t np = (size_t)im->cfg.subpalette_count * im->cfg.subpalette_size * 3;
+    std::vector<uint8_t> buf(np + NTILES + NPIX);
+    RET(set_device(im->ctx));
+    cudaStream_t st = im->ctx->stream;
+    CK(cudaMemcpyAsync(buf.data(), im->dev.palette, np, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(buf.data() + np, im->dev.tile_pal, NTILES, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(buf.data() + np + NTILES, im->dev.map, NPIX, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (uint8_t b : buf) h = (h ^ b) * 0x100000001b3ull;
+    *out = h;
+    return SNES_OK;
 }
 
 // lib.rs:579-625 + serde_json Value::to_string(): compact, object keys in BTreeMap (sorted) order.
@@ -1140,11 +1144,19 @@ static int check_slot(const snes_config &cfg, int palette, int index) {
 }
 
 static int eval_candidates_dev(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index, const uint8_t *d_cand,
-                               int ncand, int cand_idx_base, double *d_scores, snes_best *d_best, bool with_error) {
+                               int ncand, int cand_idx_base, double *d_scores, snes_best *d_best, bool with_error,
+                               int cand_stride = 0, int cand_lo = 0) {
     RET(bind_images(ctx, images, nimg));
     const snes_config cfg = images[0]->cfg;
     RET(check_slot(cfg, palette, index));
-    if (!d_cand || ncand < 1) return fail(SNES_E_INVALID, "snes_batch_eval_candidates_dev: no candidates");
+    if (!d_cand || ncand < 0) return fail(SNES_E_INVALID, "snes_batch_eval_candidates_dev: no candidates");
+    if (cand_stride && (cand_lo < 0 || cand_lo + ncand > cand_stride)) return fail(SNES_E_INVALID, "candidate slice outside the list");
+    if (ncand == 0) {
+        // an empty slice (more ranks than candidates): nothing to evaluate; the records say so (idx -1 never wins the merge)
+        if (with_error) RET(batch_error(ctx, images, nimg));
+        if (d_best) LAUNCH(ctx, "k_no_best", k_no_best<<<(nimg + 127) / 128, 128, 0, ctx->stream>>>(reinterpret_cast<Best *>(d_best), nimg));
+        return SNES_OK;
+    }
     RET(ensure_evals(ctx, (size_t)nimg * ncand));
     if (with_error && ctx->fused != 3) RET(batch_error(ctx, images, nimg));
     EvalPlan pl;
@@ -1152,6 +1164,8 @@ static int eval_candidates_dev(snes_ctx *ctx, snes_image *const *images, int nim
     pl.ncand = ncand;
     pl.ovr = palette * cfg.subpalette_size + index;
     pl.d_cand = d_cand;
+    pl.cand_stride = cand_stride;
+    pl.cand_lo = cand_lo;
     pl.do_assign = pl.do_score = true;
     pl.d_scores = d_scores ? d_scores : ctx->scores;
     pl.with_self_error = with_error && ctx->fused == 3;
@@ -1172,6 +1186,13 @@ extern "C" int snes_batch_error_eval_candidates_dev(snes_ctx *ctx, snes_image *c
                                                     const uint8_t *d_cand, int ncand, int cand_idx_base, double *d_scores,
                                                     snes_best *d_best) {
     return eval_candidates_dev(ctx, images, nimg, palette, index, d_cand, ncand, cand_idx_base, d_scores, d_best, true);
+}
+
+extern "C" int snes_batch_error_eval_candidates_slice_dev(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
+                                                          const uint8_t *d_cand_all, int ncand_all, int cand_lo, int ncand,
+                                                          double *d_scores, snes_best *d_best) {
+    if (ncand_all < 1) return fail(SNES_E_INVALID, "snes_batch_error_eval_candidates_slice_dev: no candidates");
+    return eval_candidates_dev(ctx, images, nimg, palette, index, d_cand_all, ncand, cand_lo, d_scores, d_best, true, ncand_all, cand_lo);
 }
 
 extern "C" int snes_batch_eval_candidates(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
@@ -1234,8 +1255,8 @@ static int upload_moves(snes_ctx *ctx, const snes_config &cfg, const int32_t *mo
 
 static int eval_tile_moves(snes_ctx *ctx, snes_image *const *images, int nimg, const snes_config &cfg, const TileMove *d_moves,
                            int nmoves, uint8_t *d_maps) {
-    if (!ctx->fused || cfg.subpalette_count * cfg.subpalette_size > 255)
-        return fail(SNES_E_INVALID, "tile moves need a fused scorer and subpalette_count * subpalette_size <= 255");
+    if (cfg.subpalette_count * cfg.subpalette_size > 255)
+        return fail(SNES_E_INVALID, "tile moves need subpalette_count * subpalette_size <= 255");
     EvalPlan pl;
     pl.nimg = nimg;
     pl.ncand = nmoves;
@@ -1301,10 +1322,10 @@ extern "C" int snes_batch_step_tile_moves(snes_ctx *ctx, snes_image *const *imag
     return rc;
 }
 
-extern "C" int snes_merge_best_dev(snes_ctx *ctx, const snes_best *d_gathered, int nranks, int nimg, snes_best *d_out) {
-    if (!ctx || !d_gathered || !d_out || nranks < 1 || nimg < 1) return fail(SNES_E_INVALID, "snes_merge_best_dev: bad argument");
+extern "C" int snes_merge_best_dev(snes_ctx *ctx, const snes_best *d_gathered, int nranks, int rank_stride, int nimg, snes_best *d_out) {
+    if (!ctx || !d_gathered || !d_out || nranks < 1 || nimg < 1 || rank_stride < nimg) return fail(SNES_E_INVALID, "snes_merge_best_dev: bad argument");
     RET(set_device(ctx));
-    LAUNCH(ctx, "k_merge_best", k_merge_best<<<(nimg + 127) / 128, 128, 0, ctx->stream>>>(reinterpret_cast<const Best *>(d_gathered), nranks, nimg,
+    LAUNCH(ctx, "k_merge_best", k_merge_best<<<(nimg + 127) / 128, 128, 0, ctx->stream>>>(reinterpret_cast<const Best *>(d_gathered), nranks, rank_stride, nimg,
                                                            reinterpret_cast<Best *>(d_out)));
     return SNES_OK;
 }
@@ -1355,6 +1376,45 @@ static int batch_step(snes_ctx *ctx, snes_image *const *images, int nimg, int pa
     RET(run_plan(ctx, cfg, pl));
     LAUNCH(ctx, "k_argmin", k_argmin<<<nimg, 128, 0, st>>>(ctx->scores, ncand, 0, ctx->best));
     LAUNCH(ctx, "k_apply_best", k_apply_best<<<(nimg + 127) / 128, 128, 0, st>>>(ctx->d_imgs, nimg, slot, ctx->cand, ncand, ctx->best, mode == 1));
+    RET(batch_optimize(ctx, images, nimg));
+    if (best) CK(cudaMemcpyAsync(best, ctx->best, sizeof(Best) * nimg, cudaMemcpyDeviceToHost, st));
+    if (errors_after) {
+        RET(batch_error(ctx, images, nimg));
+        CK(cudaMemcpyAsync(errors_after, ctx->self_scores, sizeof(double) * nimg, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return SNES_OK;
+}
+
+// ---- one optimiser step sharded over the GPUs of a box, host buffers in and out -------------------
+// The collective in the middle (an all-gather of 16 bytes per image and rank) belongs to the caller's process group;
+// the library provides the two halves around it and keeps the candidate list on the device in between.
+extern "C" int snes_batch_step_random_shard_begin(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
+                                                  const uint8_t *cand, int ncand_all, int cand_lo, int ncand,
+                                                  snes_best *d_best_local) {
+    RET(bind_images(ctx, images, nimg));
+    if (!cand || ncand_all < 1 || !d_best_local) return fail(SNES_E_INVALID, "snes_batch_step_random_shard_begin: bad argument");
+    const size_t E = (size_t)nimg * ncand_all;
+    for (size_t i = 0; i < E * 3; i++)
+        if (cand[i] > 32) return fail(SNES_E_INVALID, "colour component > 32");
+    RET(ensure_evals(ctx, E));
+    CK(cudaMemcpyAsync(ctx->cand, cand, E * 3, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->shard_ncand_all = ncand_all;
+    return eval_candidates_dev(ctx, images, nimg, palette, index, ctx->cand, ncand, cand_lo, nullptr, d_best_local, true, ncand_all, cand_lo);
+}
+
+extern "C" int snes_batch_step_random_shard_end(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index,
+                                                const snes_best *d_gathered, int nranks, int rank_stride, snes_best *best,
+                                                double *errors_after) {
+    RET(bind_images(ctx, images, nimg));
+    const snes_config cfg = images[0]->cfg;
+    RET(check_slot(cfg, palette, index));
+    if (!d_gathered || nranks < 1 || rank_stride < nimg || ctx->shard_ncand_all < 1)
+        return fail(SNES_E_INVALID, "snes_batch_step_random_shard_end: bad argument (or no _begin before it)");
+    cudaStream_t st = ctx->stream;
+    LAUNCH(ctx, "k_merge_best", k_merge_best<<<(nimg + 127) / 128, 128, 0, st>>>(reinterpret_cast<const Best *>(d_gathered), nranks, rank_stride, nimg, ctx->best));
+    LAUNCH(ctx, "k_apply_best", k_apply_best<<<(nimg + 127) / 128, 128, 0, st>>>(ctx->d_imgs, nimg, palette * cfg.subpalette_size + index, ctx->cand,
+                                                           ctx->shard_ncand_all, ctx->best, cfg.nes ? 1 : 0));
     RET(batch_optimize(ctx, images, nimg));
     if (best) CK(cudaMemcpyAsync(best, ctx->best, sizeof(Best) * nimg, cudaMemcpyDeviceToHost, st));
     if (errors_after) {

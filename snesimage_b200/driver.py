@@ -2,13 +2,20 @@
 SDL window, for one image or a batch of independent images, on one GPU or sharded over the GPUs of
 one box (one process per GPU, `torch.distributed`).
 
-Sharding: the candidate evaluations of one optimiser step are independent, so rank r
-evaluates the candidate slice [r*n/R, (r+1)*n/R) of every image.  The only exchange is the argmin:
-each rank's per-image (error, global candidate index) pair -- 16 bytes per image -- is all-gathered
-(NCCL over NVLink on GPUs, gloo in the CPU tests of the host logic) and every rank takes the same
-lexicographic minimum, which reproduces the reference's strict-`<`, lowest-index-wins rule
-(lib.rs:216) for any R.  Every rank then applies the accept rule to its own replica of the images, so
-replicas stay bit-identical without further communication.
+Sharding: a step's evaluations are independent across images AND across the candidates
+of one image, so the ranks form a grid of image groups x candidate slices (`plan_shards`):
+
+  * while there are at least as many images as ranks, every rank owns a contiguous block of images outright
+    -- it alone holds them, evaluates all their candidates and does their per-image bookkeeping (`error()`, the
+    delta-assignment preparation, the final `optimize()`), so nothing is replicated;
+  * ranks left over (fewer images than ranks, e.g. one picture on eight GPUs) split the candidate list of their
+    group's images: rank slice s evaluates candidates [s*n/R, (s+1)*n/R) in place from the full list.
+
+The one exchange per step is the argmin: each rank's per-image (error, global candidate index) record -- 16 bytes
+per image -- is all-gathered (NCCL over NVLink on GPUs, gloo in the CPU tests of the host logic) and the ranks of a
+group take the same lexicographic minimum, which reproduces the reference's strict-`<`, lowest-index-wins rule
+(lib.rs:216) for any slice count.  Every rank of a group then applies the accept rule to its replica of the group's
+images, so replicas stay bit-identical without further communication (checked by `state_checksums`).
 
 torch is plumbing here (device buffers, streams, the process group); the arithmetic is libsnesgpu's.
 """
@@ -52,8 +59,46 @@ class Cursor:
 
 
 def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
-    """Contiguous candidate slice of `rank`: [rank*n/world, (rank+1)*n/world)."""
+    """Contiguous slice of `rank` out of n items: [rank*n/world, (rank+1)*n/world) (may be empty when n < world)."""
     return (rank * n) // world, ((rank + 1) * n) // world
+
+
+@dataclass(frozen=True)
+class ShardPlan:
+    """Where one rank sits in the (image group x candidate slice) grid of a job."""
+    nimg: int          # images of the whole job
+    rank: int
+    world: int
+    img_groups: int    # groups the images are split into
+    cand_ranks: int    # ranks sharing one group's images, each with a slice of the candidates
+    group: int         # this rank's image group
+    slice: int         # this rank's candidate slice within the group
+    img_lo: int        # this group's images: [img_lo, img_hi)
+    img_hi: int
+    slots: int         # records per rank in the all-gather (= the largest group; smaller groups pad)
+
+    @property
+    def nloc(self) -> int:
+        return self.img_hi - self.img_lo
+
+    @property
+    def first_rank_of_group(self) -> int:
+        return self.group * self.cand_ranks
+
+    def describe(self) -> str:
+        return f"{self.img_groups} image groups x {self.cand_ranks} candidate slices"
+
+
+def plan_shards(nimg: int, rank: int, world: int, mode: str = "hybrid") -> ShardPlan:
+    """mode "hybrid": as many image groups as divide the world and do not exceed nimg, the rest of the ranks slice the
+    candidates; mode "candidates": one group, every rank holds every image (the replicated layout)."""
+    if nimg < 1 or not (0 <= rank < world):
+        raise ValueError("plan_shards: bad arguments")
+    groups = 1 if mode == "candidates" else max(d for d in range(1, world + 1) if world % d == 0 and d <= nimg)
+    cand_ranks = world // groups
+    group, sl = rank // cand_ranks, rank % cand_ranks
+    lo, hi = shard_bounds(nimg, group, groups)
+    return ShardPlan(nimg, rank, world, groups, cand_ranks, group, sl, lo, hi, -(-nimg // groups))
 
 
 def merge_best_host(gathered: np.ndarray) -> np.ndarray:
@@ -68,26 +113,28 @@ def merge_best_host(gathered: np.ndarray) -> np.ndarray:
 
 
 class BatchOptimizer:
-    """A batch of independent OptimizedImages advancing through the reference's schedule together,
-    with the candidates of every step sharded over the ranks of `group`."""
+    """A batch of independent OptimizedImages advancing through the reference's schedule together.  `images` are the
+    images THIS rank holds (plan.img_lo .. plan.img_hi of the job); with the default single-rank plan, all of them."""
 
-    def __init__(self, ctx: engine.Context, images: Sequence[engine.OptimizedImage], rank: int = 0, world: int = 1,
+    def __init__(self, ctx: engine.Context, images: Sequence[engine.OptimizedImage], plan: Optional[ShardPlan] = None,
                  group=None, seed: int = 0):
         import torch
         self.torch = torch
         self.ctx = ctx
         self.images = list(images)
+        self.plan = plan or plan_shards(len(self.images), 0, 1)
+        if len(self.images) != self.plan.nloc:
+            raise ValueError(f"rank {self.plan.rank} holds {len(self.images)} images, its plan says {self.plan.nloc}")
         self.config = self.images[0].config
-        self.rank, self.world, self.group = rank, world, group
+        self.group = group
         self.seed = seed
         self.cursor = Cursor()
         self.iteration = 0
         self.device = torch.device("cuda", ctx.device)
-        nimg = len(self.images)
-        self._best_local = torch.zeros(nimg * 2, dtype=torch.int64, device=self.device)   # nimg x 16 bytes
-        self._best_all = torch.zeros(world * nimg * 2, dtype=torch.int64, device=self.device)
-        self._best = torch.zeros(nimg * 2, dtype=torch.int64, device=self.device)
-        self._errors = torch.zeros(nimg, dtype=torch.float64, device=self.device)
+        slots, world = self.plan.slots, self.plan.world
+        self._best_local = torch.zeros(slots * 2, dtype=torch.int64, device=self.device)   # slots x 16 bytes
+        self._best_all = torch.zeros(world * slots * 2, dtype=torch.int64, device=self.device)
+        self._best = torch.zeros(slots * 2, dtype=torch.int64, device=self.device)
         # enqueue library work on torch's current stream so it orders with the collectives and is seen by
         # torch.cuda.Event timing; torch reports the legacy default stream as handle 0, which the C ABI reads as
         # "own stream", so name it explicitly (cudaStreamLegacy == 0x1)
@@ -95,42 +142,73 @@ class BatchOptimizer:
 
     # ---- candidate lists ---------------------------------------------------------------------------
     def candidates_host(self, ncand_total: int) -> np.ndarray:
-        """The explicit, seeded stand-in for the 64 rand::rng() draws of lib.rs:205-208, per image."""
-        return np.stack([synth.candidates(self.seed * 1000003 + j, self.iteration, ncand_total) for j in range(len(self.images))])
+        """The explicit, seeded stand-in for the 64 rand::rng() draws of lib.rs:205-208, per local image (seeded by the
+        image's number in the whole job, so the lists do not depend on how the job is sharded)."""
+        return np.stack([synth.candidates(self.seed * 1000003 + self.plan.img_lo + j, self.iteration, ncand_total)
+                         for j in range(len(self.images))])
+
+    def _gathered_group_ptr(self) -> int:
+        """Device address of the gathered records of this rank's group (cand_ranks blocks of `slots` records)."""
+        return self._best_all.data_ptr() + self.plan.first_rank_of_group * self.plan.slots * 16
+
+    def _exchange(self):
+        """The step's one collective: all-gather of every rank's records (16 bytes per image slot)."""
+        self.torch.distributed.all_gather_into_tensor(self._best_all, self._best_local, group=self.group)
 
     # ---- one optimize_palette_entry_random over the batch, device-resident inputs ----------------------
-    def step_random_dev(self, d_cand_all, ncand_total: int):
-        """d_cand_all: uint8 CUDA tensor (nimg, ncand_total, 3), identical on every rank."""
-        torch = self.torch
-        nimg = len(self.images)
+    def begin_step_dev(self, d_cand, ncand_total: int):
+        """First half: `best_error = self.error()` (lib.rs:199) + this rank's share of the candidate loop (lib.rs:205-220)
+        in one pass; the slice is read in place from the full list and the records carry indices into the full list."""
+        pl = self.plan
         p, i = self.cursor.palette, self.cursor.palette_index
-        lo, hi = shard_bounds(ncand_total, self.rank, self.world)
-        # best_error = self.error() (lib.rs:199) + the candidate loop (lib.rs:205-220) in one pass
-        if self.world == 1:
-            engine.batch_error_eval_candidates_dev(self.images, p, i, d_cand_all.data_ptr(), ncand_total, 0, None, self._best.data_ptr())
-        else:
-            # this rank's slice, made contiguous per image
-            d_slice = d_cand_all[:, lo:hi, :].contiguous()
-            engine.batch_error_eval_candidates_dev(self.images, p, i, d_slice.data_ptr(), hi - lo, lo, None, self._best_local.data_ptr())
-            torch.distributed.all_gather_into_tensor(self._best_all, self._best_local, group=self.group)
-            engine.merge_best_dev(self.ctx, self._best_all.data_ptr(), self.world, nimg, self._best.data_ptr())
-        # accept if strictly better, then optimize() with the winner (lib.rs:216-219, 236-237)
-        engine.batch_apply_best_dev(self.images, p, i, d_cand_all.data_ptr(), ncand_total, self._best.data_ptr())
+        lo, hi = shard_bounds(ncand_total, pl.slice, pl.cand_ranks)
+        out = self._best if pl.world == 1 else self._best_local
+        engine.batch_error_eval_candidates_slice_dev(self.images, p, i, d_cand.data_ptr(), ncand_total, lo, hi - lo, None, out.data_ptr())
+
+    def end_step_dev(self, d_cand, ncand_total: int):
+        """Second half, after the exchange: merge the records of this group's ranks, accept if strictly better, optimize()
+        with the winner (lib.rs:216-219, 236-237)."""
+        pl = self.plan
+        p, i = self.cursor.palette, self.cursor.palette_index
+        if pl.world > 1:
+            engine.merge_best_dev(self.ctx, self._gathered_group_ptr(), pl.cand_ranks, pl.nloc, self._best.data_ptr(), rank_stride=pl.slots)
+        engine.batch_apply_best_dev(self.images, p, i, d_cand.data_ptr(), ncand_total, self._best.data_ptr())
         self.cursor.advance(self.config)
         self.iteration += 1
 
+    def step_random_dev(self, d_cand, ncand_total: int):
+        """d_cand: uint8 CUDA tensor (local images, ncand_total, 3): the full candidate list of this rank's images,
+        identical on the ranks of its group."""
+        self.begin_step_dev(d_cand, ncand_total)
+        if self.plan.world > 1:
+            self._exchange()
+        self.end_step_dev(d_cand, ncand_total)
+
     # ---- the same through host buffers (the call a user of the library makes) --------------------------
-    def step_random_host(self, cand_all_pinned, d_cand_all, best_pinned):
-        """cand_all_pinned: pinned CPU uint8 tensor (nimg, ncand_total, 3); d_cand_all: its device staging
-        buffer; best_pinned: pinned CPU int64 tensor (nimg*2) receiving the winning (err, idx) records."""
-        d_cand_all.copy_(cand_all_pinned, non_blocking=True)
-        self.step_random_dev(d_cand_all, cand_all_pinned.shape[1])
-        best_pinned.copy_(self._best, non_blocking=True)
-        self.torch.cuda.current_stream(self.device).synchronize()
-        return best_pinned
+    def step_random_host(self, cand_host: np.ndarray, best_host: Optional[np.ndarray] = None) -> np.ndarray:
+        """cand_host: (local images, ncand_total, 3) uint8 host array (pinned or not); returns the winning (err, idx)
+        records of the local images in host memory.  Copies in, both halves of the step, the all-gather between them and
+        the copy out are all inside this call; it returns when the stream has drained."""
+        pl = self.plan
+        p, i = self.cursor.palette, self.cursor.palette_index
+        ncand_total = cand_host.shape[1]
+        if pl.world == 1:
+            best, _ = engine.batch_step_random(self.images, p, i, cand_host)
+        else:
+            lo, hi = shard_bounds(ncand_total, pl.slice, pl.cand_ranks)
+            engine.batch_step_random_shard_begin(self.images, p, i, cand_host, lo, hi - lo, self._best_local.data_ptr())
+            self._exchange()
+            best, _ = engine.batch_step_random_shard_end(self.images, p, i, self._gathered_group_ptr(), pl.cand_ranks, pl.slots, best_host)
+        self.cursor.advance(self.config)
+        self.iteration += 1
+        return best
 
     def best_records(self) -> np.ndarray:
-        return self._best.cpu().numpy().view(engine.BEST_DTYPE)
+        return self._best.cpu().numpy().view(engine.BEST_DTYPE)[:self.plan.nloc]
+
+    def state_checksums(self) -> List[int]:
+        """64-bit checksum of (palette, tile_palettes, palette_map) of every local image."""
+        return [im.state_checksum() for im in self.images]
 
 
 def sweep_random(images: Sequence[engine.OptimizedImage], seed: int, sweep: int, ncand: int = 64) -> np.ndarray:
@@ -253,6 +331,8 @@ class HeadlessRunner:
         self.phase = self.OPTIMIZATION
 
     def iterate(self, n: int = 1):
+        if self.phase != self.OPTIMIZATION:      # lib.rs:889: the optimiser only runs in the last phase
+            return
         im, c = self.image, self.cursor
         for _ in range(n):
             mode = c.mode(self.config)

@@ -109,8 +109,12 @@ _SIGNATURES = {
     "snes_batch_eval_candidates": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "snes_batch_eval_candidates_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "snes_batch_error_eval_candidates_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
+    "snes_batch_error_eval_candidates_slice_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "snes_batch_step_random_shard_begin": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp]),
+    "snes_batch_step_random_shard_end": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
+    "snes_image_state_checksum": (_i, [_vp, C.POINTER(C.c_uint64)]),
     "snes_batch_apply_best_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
-    "snes_merge_best_dev": (_i, [_vp, _vp, _i, _i, _vp]),
+    "snes_merge_best_dev": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "snes_batch_step_random": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),
     "snes_batch_step_nes": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "snes_batch_step_channel": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
@@ -129,12 +133,13 @@ def library_path() -> str:
 
 
 def lib():
-    """Load libsnesgpu.so (building it in-tree first if it is missing).  Raises if that fails."""
+    """Load libsnesgpu.so, (re)building it in-tree first when it is missing or older than a source it is built from
+    (a no-op when fresh; on a box without nvcc a stale library is an error, not a silent old binary)."""
     global _lib
     if _lib is not None:
         return _lib
     so = os.environ.get("SNESGPU_SO") or _build.SO   # SNESGPU_SO: an instrumented debug build (scripts/phase_timing.py)
-    if so == _build.SO and not os.path.exists(so):
+    if so == _build.SO:
         _build.build_library()
     L = C.CDLL(so)
     for name, (res, args) in _SIGNATURES.items():
@@ -197,7 +202,7 @@ class Context:
         _check(self._l.snes_ctx_set_chunk(self._h, int(evaluations)), "snes_ctx_set_chunk")
 
     def set_scorer(self, fused: int = 3, block_width: int = 32, delta_assign: bool = True):
-        """fused: 3 = k_score_v3 (default), 2 = k_score_v2, 1 = k_score_fused, 0 = multi-kernel pipeline (A/B checks)."""
+        """fused: 3 = k_score_v3 (default), 2 = k_score_v2 (its predecessor, kept as the A/B check)."""
         _check(self._l.snes_ctx_set_scorer(self._h, int(fused), int(block_width), int(delta_assign)), "snes_ctx_set_scorer")
 
     def profile_begin(self):
@@ -343,6 +348,12 @@ class OptimizedImage:
     def palette_map(self, v):
         v = _u8(v, (NPIX,))
         _check(self._l.snes_image_set_palette_map(self._h, _ptr(v)), "set_palette_map")
+
+    def state_checksum(self) -> int:
+        """64-bit FNV-1a over palette, tile_palettes and palette_map."""
+        v = C.c_uint64(0)
+        _check(self._l.snes_image_state_checksum(self._h, C.byref(v)), "state_checksum")
+        return int(v.value)
 
     # ---- debug taps --------------------------------------------------------------------------------
     def debug_planes(self):
@@ -496,11 +507,46 @@ def batch_error_eval_candidates_dev(images: Sequence[OptimizedImage], palette: i
                                                        cand_idx_base, d_scores, d_best), "snes_batch_error_eval_candidates_dev")
 
 
+def batch_error_eval_candidates_slice_dev(images: Sequence[OptimizedImage], palette: int, index: int, d_cand_all: int, ncand_all: int,
+                                          cand_lo: int, ncand: int, d_scores: Optional[int] = None, d_best: Optional[int] = None):
+    """A rank's share of a candidate-sharded step: error() + candidates [cand_lo, cand_lo + ncand) of the full device list,
+    read in place; best records carry indices into the full list."""
+    ctx = _ctx_of(images)
+    _check(ctx._l.snes_batch_error_eval_candidates_slice_dev(ctx._h, _handles(images), len(images), palette, index, d_cand_all,
+                                                             ncand_all, cand_lo, ncand, d_scores, d_best),
+           "snes_batch_error_eval_candidates_slice_dev")
+
+
+def batch_step_random_shard_begin(images: Sequence[OptimizedImage], palette: int, index: int, cand, cand_lo: int, ncand: int,
+                                  d_best_local: int):
+    """First half of a sharded step with host buffers: cand (nimg, ncand_all, 3) host array -> device, error() + this
+    rank's slice, records left in d_best_local (device)."""
+    ctx = _ctx_of(images)
+    nimg = len(images)
+    cand = _u8(cand).reshape(nimg, -1, 3)
+    _check(ctx._l.snes_batch_step_random_shard_begin(ctx._h, _handles(images), nimg, palette, index, _ptr(cand), cand.shape[1],
+                                                     cand_lo, ncand, d_best_local), "snes_batch_step_random_shard_begin")
+
+
+def batch_step_random_shard_end(images: Sequence[OptimizedImage], palette: int, index: int, d_gathered: int, nranks: int,
+                                rank_stride: int, best: Optional[np.ndarray] = None, want_errors: bool = False):
+    """Second half: merge the gathered records of the ranks sharing these images, accept, optimize(); synchronous."""
+    ctx = _ctx_of(images)
+    nimg = len(images)
+    if best is None:
+        best = np.zeros(nimg, BEST_DTYPE)
+    errs = np.zeros(nimg, np.float64) if want_errors else None
+    _check(ctx._l.snes_batch_step_random_shard_end(ctx._h, _handles(images), nimg, palette, index, d_gathered, nranks, rank_stride,
+                                                   _ptr(best), _ptr(errs)), "snes_batch_step_random_shard_end")
+    return best, errs
+
+
 def batch_apply_best_dev(images: Sequence[OptimizedImage], palette: int, index: int, d_cand_all: int, ncand_all: int, d_best: int):
     ctx = _ctx_of(images)
     _check(ctx._l.snes_batch_apply_best_dev(ctx._h, _handles(images), len(images), palette, index, d_cand_all, ncand_all, d_best),
            "snes_batch_apply_best_dev")
 
 
-def merge_best_dev(ctx: Context, d_gathered: int, nranks: int, nimg: int, d_out: int):
-    _check(ctx._l.snes_merge_best_dev(ctx._h, d_gathered, nranks, nimg, d_out), "snes_merge_best_dev")
+def merge_best_dev(ctx: Context, d_gathered: int, nranks: int, nimg: int, d_out: int, rank_stride: Optional[int] = None):
+    """d_gathered: nranks blocks of records, rank r's at d_gathered + r * rank_stride * 16 (default stride: nimg)."""
+    _check(ctx._l.snes_merge_best_dev(ctx._h, d_gathered, nranks, rank_stride or nimg, nimg, d_out), "snes_merge_best_dev")

@@ -1,7 +1,7 @@
 """Synthetic inputs for the palette-optimisation hot path.
 
 Counter-based, integer-only generators built on the splitmix64 finaliser, so the same bytes can be
-reproduced in any language (the C++ CLI in csrc/host restates `mix64`/`hashn`).  The reference
+reproduced in any language (tests/golden/gen_reference_vectors.rs restates `mix64`/`hashn` in Rust).  The reference
 itself ships no sample image and draws its candidates from an unseeded `rand::rng()`
 (/root/reference/src/lib.rs:201-208); here the candidate list is an explicit, seeded input.
 """

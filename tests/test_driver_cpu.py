@@ -60,6 +60,51 @@ def test_shard_bounds_partition():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
 
 
+def test_plan_shards_covers_every_image_and_candidate_once():
+    """The (image group x candidate slice) grid: every (image, candidate) pair belongs to exactly one rank, images go to
+    whole ranks while there are enough of them, and the all-gather slot count fits the largest group."""
+    for nimg, world, ncand in [(64, 1, 64), (64, 2, 64), (64, 4, 64), (64, 8, 64), (1, 8, 64), (4, 8, 64), (5, 2, 7), (3, 8, 2), (6, 4, 1)]:
+        plans = [driver.plan_shards(nimg, r, world) for r in range(world)]
+        seen = np.zeros((nimg, ncand), np.int32)
+        for pl in plans:
+            assert pl.img_groups * pl.cand_ranks == world and pl.img_groups <= nimg
+            assert pl.nloc <= pl.slots and pl.first_rank_of_group + pl.slice == pl.rank
+            lo, hi = driver.shard_bounds(ncand, pl.slice, pl.cand_ranks)
+            seen[pl.img_lo:pl.img_hi, lo:hi] += 1
+        assert (seen == 1).all(), (nimg, world, ncand)
+        if nimg >= world:
+            assert plans[0].cand_ranks == 1          # enough images: nothing is replicated
+        # the replicated layout of round 1 stays available
+        pc = driver.plan_shards(nimg, world - 1, world, "candidates")
+        assert (pc.img_groups, pc.cand_ranks, pc.img_lo, pc.img_hi, pc.slice) == (1, world, 0, nimg, world - 1)
+    with pytest.raises(ValueError):
+        driver.plan_shards(4, 2, 2)
+
+
+def test_bench_relaunch_keeps_the_json_line_on_stdout(tmp_path):
+    """`python bench.py --gpus N` outside torchrun relaunches itself under torch.distributed.run; the child must inherit the
+    real stdout (the parent used to point fd 1 at stderr first, so the line went to stderr).  A stub stands in
+    for the launcher: it runs the same bench.py in the reference arm, whose line must arrive on the parent's stdout."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    stub = tmp_path / "launcher_stub.py"
+    stub.write_text(
+        "import os, subprocess, sys\n"
+        "args = sys.argv[1:]\n"
+        "script = next(i for i, a in enumerate(args) if a.endswith('bench.py'))\n"
+        "os.environ['WORLD_SIZE'] = '2'\n"           # what torchrun would set; the child then skips the relaunch
+        "sys.exit(subprocess.call([sys.executable, args[script], '--impl', 'reference', '--steps', '1', '--warmup', '1']))\n")
+    env = dict(os.environ, BENCH_LAUNCHER=str(stub))
+    env.pop("WORLD_SIZE", None)
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--gpus", "2"], capture_output=True, text=True, timeout=600,
+                         cwd=root, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = out.stdout.strip().splitlines()
+    assert len(lines) == 1 and json.loads(lines[0])["impl"] == "reference", (out.stdout[:300], out.stderr[-300:])
+
+
 def test_merge_best_is_first_minimum():
     rng = np.random.RandomState(0)
     nimg, ncand, world = 9, 24, 4
@@ -95,32 +140,49 @@ def _gloo_worker(rank, world, port, nimg, ncand, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    # every rank derives the same full score table, evaluates only its slice, then all-gathers 16-byte records
+    # every rank derives the same full score table, evaluates only its share of the (image group x candidate slice) grid,
+    # then all-gathers 16-byte records, padded to the plan's slot count
     scores = (synth.hashn(3, np.arange(nimg)[:, None], np.arange(ncand)[None, :]) % np.uint64(5)).astype(np.float64)
-    lo, hi = driver.shard_bounds(ncand, rank, world)
-    local = np.zeros(nimg, engine.BEST_DTYPE)
-    k = np.argmin(scores[:, lo:hi], axis=1)
-    local["idx"] = lo + k
-    local["err"] = scores[np.arange(nimg), lo + k]
+    pl = driver.plan_shards(nimg, rank, world)
+    lo, hi = driver.shard_bounds(ncand, pl.slice, pl.cand_ranks)
+    local = np.zeros(pl.slots, engine.BEST_DTYPE)
+    local["idx"] = -1
+    if hi > lo:
+        mine = scores[pl.img_lo:pl.img_hi, lo:hi]
+        k = np.argmin(mine, axis=1)
+        local["idx"][:pl.nloc] = lo + k
+        local["err"][:pl.nloc] = mine[np.arange(pl.nloc), k]
     t_local = torch.from_numpy(local.view(np.int64).copy())
-    t_all = torch.zeros(world * nimg * 2, dtype=torch.int64)
+    t_all = torch.zeros(world * pl.slots * 2, dtype=torch.int64)
     dist.all_gather_into_tensor(t_all, t_local)
-    merged = driver.merge_best_host(t_all.numpy().view(engine.BEST_DTYPE).reshape(world, nimg))
-    ok = np.array_equal(merged["idx"], np.argmin(scores, axis=1))
-    res = torch.tensor([int(ok), int(merged["idx"].sum())])
-    gathered = [torch.zeros_like(res) for _ in range(world)]
-    dist.all_gather(gathered, res)
+    gathered = t_all.numpy().view(engine.BEST_DTYPE).reshape(world, pl.slots)
+    # the records of this rank's group decide its images; every rank can also rebuild the whole job's winners
+    first = pl.first_rank_of_group
+    merged = driver.merge_best_host(gathered[first:first + pl.cand_ranks])[:pl.nloc]
+    ok = np.array_equal(merged["idx"], np.argmin(scores[pl.img_lo:pl.img_hi], axis=1))
+    whole = []
+    for g in range(pl.img_groups):
+        glo, ghi = driver.shard_bounds(nimg, g, pl.img_groups)
+        whole.append(driver.merge_best_host(gathered[g * pl.cand_ranks:(g + 1) * pl.cand_ranks])[:ghi - glo])
+    whole = np.concatenate(whole)
+    ok = ok and np.array_equal(whole["idx"], np.argmin(scores, axis=1))
+    res = torch.tensor([int(ok), int(whole["idx"].sum())])
+    got = [torch.zeros_like(res) for _ in range(world)]
+    dist.all_gather(got, res)
     if rank == 0:
-        out.put([g.tolist() for g in gathered])
+        out.put([g.tolist() for g in got])
     dist.destroy_process_group()
 
 
-def test_argmin_over_gloo_world_size_2():
+@pytest.mark.parametrize("nimg,ncand", [(16, 64), (1, 64), (3, 1)])
+def test_argmin_over_gloo_world_size_2(nimg, ncand):
+    """world_size 2 over gloo: 16 images -> two image groups (no slicing); one image -> two candidate slices of it;
+    three images -> groups of 1 and 2 images (padded records)."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, 16, 64, out)) for r in range(2)]
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, nimg, ncand, out)) for r in range(2)]
     for p in procs:
         p.start()
     res = out.get(timeout=120)
@@ -147,6 +209,14 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["metric"].startswith("candidate palette evals/sec") and "workload" in line["config"]
+    # both arms build `config` with one function, so the driver's same_config check compares like with like
+    import argparse
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    ns = argparse.Namespace(nimg=bench.NIMG, ncand=bench.NCAND, chunk=4096)
+    assert line["config"] == bench.build_config(ns, 1)
 
 
 def test_vertical_chain_thread_mapping_covers_every_plane_column_once():
