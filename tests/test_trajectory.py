@@ -1,0 +1,171 @@
+"""Step-by-step GPU-vs-oracle parity of the optimiser at the sizes BASELINE.json names (configs[0..3]):
+
+  cfg1  8 x 15, RGB distance, no dither            cfg2  --perceptual-palettes (CIELAB), 4 x 7
+  cfg3  --dither, 8 x 15                            cfg4  --nes --dither, 4 x 3
+
+k-means init + tile assignment, then ITERATIONS iterations of the schedule of run() (lib.rs:889-933), the state compared
+with the oracle's after EVERY iteration.  The oracle's 64 (56) candidate evaluations of an iteration are farmed over the
+host cores (one oracle image per worker process; `OraclePool`), so a config costs seconds instead of minutes.
+
+RGB metric (cfg1, cfg3, cfg4): palette, tile_palettes and palette_map bit-identical after every iteration; error within
+1e-8.  CIELAB (cfg2): CUDA's transcendentals differ from glibc's by ulps, so a handful of pixels may choose another
+entry of (to the oracle) equal distance: every candidate's score must agree within SCORE_TOL = 1e-4 and the decision
+(argmin, accept) must be identical whenever the oracle's margin exceeds the tolerance (SURVEY.md 7 "Argmin stability");
+after a permitted divergence the oracle continues from the GPU's state.
+"""
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from snesimage_b200 import driver, engine, synth
+from util import OraclePool, lab_choice_ok, oracle_entry_step
+
+pytestmark = pytest.mark.gpu
+
+ITERATIONS = 24
+SCORE_TOL = 1e-4
+TIGHT_TOL = 1e-8
+LAB_TOL = 2e-4
+
+CONFIGS = {
+    "cfg1": dict(subpalette_count=8, subpalette_size=15),
+    "cfg2": dict(subpalette_count=4, subpalette_size=7, perceptual_palettes=True),
+    "cfg3": dict(subpalette_count=8, subpalette_size=15, dither=True),
+    "cfg4": dict(subpalette_count=4, subpalette_size=3, nes=True, dither=True),
+}
+
+
+def _oracle(rgba, cfg):
+    return ob.OracleImage(rgba, cfg.subpalette_count, cfg.subpalette_size, cfg.dither, cfg.perceptual_palettes, cfg.nes)
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg3", "cfg4"])
+def test_trajectory_rgb_metric_bit_exact(ctx, name):
+    cfg = engine.Config(**CONFIGS[name])
+    rgba = synth.image(0, "V")
+    r = driver.HeadlessRunner(ctx, rgba, cfg, seed=0, ncand=64)
+    o = _oracle(rgba, cfg)
+    r.initialize()
+    o.initialize_tiles()
+    o.recalculate_palettes()
+    assert np.array_equal(r.image.tile_palettes, o.tile_palettes)
+    assert np.array_equal(r.image.palette, o.palette) and np.array_equal(r.image.palette_map, o.palette_map)
+    cur = driver.Cursor()
+    accepted = 0
+    with OraclePool(rgba, cfg) as pool:
+        for it in range(ITERATIONS):
+            before = o.palette.copy()
+            oracle_entry_step(o, pool, cur.mode(cfg), cur.palette, cur.palette_index, cur.channel, synth.candidates(0, it, 64))
+            o.optimize()                                   # lib.rs:906-908
+            accepted += int(not np.array_equal(before, o.palette))
+            cur.advance(cfg)
+            r.iterate(1)
+            assert np.array_equal(r.image.palette, o.palette), (name, it)
+            assert np.array_equal(r.image.palette_map, o.palette_map), (name, it)
+            assert abs(r.last_error - o.error()) <= TIGHT_TOL, (name, it)
+    assert np.array_equal(r.image.tile_palettes, o.tile_palettes)
+    assert r.image.as_json() == o.as_json()
+    assert (r.cursor.palette, r.cursor.palette_index, r.cursor.step) == (cur.palette, cur.palette_index, cur.step)
+    assert accepted >= 3, "the trajectory should move: most early iterations find a better colour"
+    r.image.close()
+
+
+def test_trajectory_cielab_within_tolerance(ctx):
+    """cfg2.  Per iteration: GPU scores of all 64 candidates against the oracle's on the same state within SCORE_TOL; the
+    chosen candidate and the accept decision identical whenever the oracle's margins exceed 2 * SCORE_TOL; palette_maps
+    differ only where the oracle rates both entries within LAB_TOL."""
+    name = "cfg2"
+    cfg = engine.Config(**CONFIGS[name])
+    S = cfg.subpalette_size
+    rgba = synth.image(0, "V")
+    r = driver.HeadlessRunner(ctx, rgba, cfg, seed=0, ncand=64)
+    o = _oracle(rgba, cfg)
+    r.initialize()
+    o.initialize_tiles()
+    o.recalculate_palettes()
+    assert np.array_equal(r.image.tile_palettes, o.tile_palettes)
+    # Lab cluster sums are f64 sums of non-integers in another (fixed) order and cbrt differs in the last ulp: at most one
+    # entry may land on the neighbouring 5-bit step; the oracle then continues from the GPU's palette
+    dp = np.abs(r.image.palette.astype(int) - o.palette.astype(int))
+    assert dp.max() <= 1 and (dp.sum(axis=1) > 0).sum() <= 1
+    o.palette = r.image.palette
+    o.optimize()
+    cur = driver.Cursor()
+    resyncs = decided = 0
+    with OraclePool(rgba, cfg) as pool:
+        for it in range(ITERATIONS):
+            assert cur.mode(cfg) == "random"
+            p, i = cur.palette, cur.palette_index
+            cand = synth.candidates(0, it, 64)
+            # same state on both sides (palette, tile_palettes; the maps agree up to LAB_TOL choices)
+            ndiff, worst = lab_choice_ok(o, r.image.palette_map, LAB_TOL)
+            assert worst <= LAB_TOL and ndiff <= 65536 // 1000, (it, ndiff, worst)
+            so = pool.eval(o.palette, o.tile_palettes, p, i, cand)
+            sg = r.image.eval_candidates(p, i, cand)
+            assert np.max(np.abs(sg - so)) <= SCORE_TOL, (it, float(np.max(np.abs(sg - so))))
+            eo, eg = o.error(), r.image.error()
+            assert abs(eo - eg) <= SCORE_TOL
+            ko = int(np.argmin(so))
+            rest = np.delete(so, ko)
+            margin = min(float(rest.min() - so[ko]), abs(float(so[ko] - eo)))   # runner-up gap and accept gap
+            # the GPU's own step
+            r.iterate(1)
+            take = so[ko] < eo
+            want = o.palette.copy()
+            if take:
+                want[p * S + i] = cand[ko]
+            if margin > 2 * SCORE_TOL:
+                decided += 1
+                assert np.array_equal(r.image.palette, want), (it, margin)
+            elif not np.array_equal(r.image.palette, want):
+                resyncs += 1                               # a permitted divergence: scores equal within the tolerance
+            o.palette = r.image.palette
+            o.optimize()
+            cur.advance(cfg)
+    assert decided >= ITERATIONS // 2, "most iterations must have a clear winner, or the test proves nothing"
+    assert resyncs <= 2
+    r.image.close()
+
+
+def test_fuzz_parity_short(ctx):
+    """A short run of scripts/fuzz_parity.py's sweep: random (family, C, S, dither, NES, seed); k-means init, candidate
+    evaluations and one optimiser step of each kind; integer outputs identical, errors within 1e-8."""
+    rng = np.random.default_rng(7)
+    for case in range(6):
+        family = "VGBT"[int(rng.integers(4))]
+        C, S = int(rng.integers(1, 9)), int(rng.integers(2, 16))
+        dither, nes = bool(rng.integers(2)), bool(rng.integers(4) == 0)
+        seed = int(rng.integers(1 << 20))
+        rgba = synth.image(seed, family)
+        cfg = engine.Config(subpalette_count=C, subpalette_size=S, dither=dither, nes=nes)
+        g = engine.OptimizedImage(ctx, rgba, cfg)
+        o = _oracle(rgba, cfg)
+        tag = f"case {case}: {family} C={C} S={S} dither={dither} nes={nes} seed={seed}"
+        try:
+            try:
+                o.initialize_tiles()
+                o.recalculate_palettes()
+            except RuntimeError:
+                with pytest.raises(engine.KmeansAssertion):
+                    g.initialize_tiles()
+                    g.recalculate_palettes()
+                continue
+            g.initialize_tiles()
+            g.recalculate_palettes()
+            assert np.array_equal(g.tile_palettes, o.tile_palettes) and np.array_equal(g.palette, o.palette), tag
+            assert np.array_equal(g.palette_map, o.palette_map), tag
+            p, i = int(rng.integers(C)), int(rng.integers(S))
+            cand = synth.candidates(seed, case, 4)
+            sg = engine.batch_eval_candidates([g], p, i, cand[None])["scores"][0]
+            assert np.max(np.abs(sg - o.eval_candidates(p, i, cand))) <= TIGHT_TOL, tag
+            if nes:
+                g.optimize_palette_entry_nes(p, i)
+                o.optimize_palette_entry_nes(p, i)
+            else:
+                g.optimize_palette_entry_random(p, i, cand)
+                o.optimize_palette_entry_random(p, i, cand)
+            assert np.array_equal(g.palette, o.palette) and np.array_equal(g.palette_map, o.palette_map), tag
+            assert abs(g.error() - o.error()) <= TIGHT_TOL, tag
+            assert g.as_json() == o.as_json(), tag
+        finally:
+            g.close()
