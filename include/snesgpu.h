@@ -57,6 +57,14 @@ typedef struct snes_best {
     int32_t pad;
 } snes_best;
 
+/* One iteration of the optimiser loop of run() (lib.rs:889-933) names a palette entry (and, in channel mode, a channel). */
+typedef struct snes_step {
+    int32_t palette;   /* subpalette, 0 .. subpalette_count-1 */
+    int32_t index;     /* entry within it, 0 .. subpalette_size-1 */
+    int32_t channel;   /* 0 r, 1 g, 2 b: optimize_palette_entry_channel only */
+    int32_t reserved;
+} snes_step;
+
 const char *snes_last_error(void);
 int snes_version(void);
 
@@ -186,6 +194,25 @@ int snes_batch_step_nes(snes_ctx *ctx, snes_image *const *images, int nimg, int 
                         double *errors_after);
 int snes_batch_step_channel(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index, int channel,
                             snes_best *best, double *errors_after);
+
+/* ---- several palette entries per launch (lib.rs:889-933 looked at as a whole; TODO.md:33-35) --------- */
+/* Candidates of nsteps palette entries evaluated against ONE state in one launch sequence: for image j, step s and candidate
+ * k: colours[steps[s]] = cand[j][s][k]; optimize(); error().  cand: nimg*nsteps*ncand*3; scores[nimg*nsteps*ncand] and
+ * best[nimg*nsteps] (strict-< first minimum of each step's list, idx within that list) are optional.  The images' own state
+ * is not modified.  With every entry of the palette as a step this is the whole-sweep batch TODO.md:33-35 wishes for. */
+int snes_batch_eval_candidates_multi(snes_ctx *ctx, snes_image *const *images, int nimg, const snes_step *steps, int nsteps,
+                                     const uint8_t *cand, int ncand, double *scores, snes_best *best);
+/* nsteps consecutive iterations of the loop body of run() (lib.rs:889-910: optimize_palette_entry_* + optimize() + error())
+ * in one call, exactly the reference's trajectory: all steps' candidates are evaluated against the current state, then the
+ * steps are taken in order up to and including the first one that accepts a candidate (an iteration that accepts nothing
+ * leaves the state it was evaluated against, so evaluating the next one early changes nothing).  mode 0: random, cand =
+ * nsteps*ncand*3 explicit colours (the reference's rand::rng() draws, lib.rs:205-208); 1: NES (one step per call: it always
+ * replaces the entry, lib.rs:250); 2: channel (32 values of steps[s].channel).  *consumed = iterations the call stands for
+ * (the caller advances its cursor by that many and drops the rest of the list), *error_before = error() of the state the
+ * call started from (what every iteration before the accepting one ends with; not computed in NES mode), *error_after =
+ * error() of the new state. */
+int snes_image_iterate(snes_image *im, int mode, const snes_step *steps, int nsteps, const uint8_t *cand, int ncand,
+                       int *consumed, double *error_before, double *error_after);
 
 /* ---- tile reassignment as evaluated candidates ------------------------------------------------ */
 /* The reference changes a tile's subpalette only by hand (a click cycles it, lib.rs:1005-1017; TODO.md:36-37 wishes for

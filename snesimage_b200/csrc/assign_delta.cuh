@@ -1,17 +1,20 @@
 // Candidate evaluation without dithering: optimize() (lib.rs:425-501) restricted to what a candidate can change.
 //
-// A candidate replaces ONE entry (slot `ovr` = palette*S + index) of the image's palette
+// A candidate replaces ONE entry (slot = palette*S + index) of the image's palette
 // (lib.rs:205-220, 252-262, 296-306).  Without error diffusion every pixel is decided on its own
 // (lib.rs:447-451), so only pixels of tiles bound to that subpalette can change, and for those the
 // reference's strict-< first-minimum over the S entries equals
 //        combine( first-minimum over the entries j != index  ,  the candidate's own distance )
-// with ties going to the lower index.  The first part does not depend on the candidate:
+// with ties going to the lower index.  The first part does not depend on the candidate's colour, and it follows from
+// two per-pixel records that do not depend on the replaced entry either: the pixel's best entry (first minimum over
+// all S) and its runner-up (first minimum over the entries other than the best).  The first minimum over j != index
+// is the best when best != index, and the runner-up otherwise.
 //
 //   k_assign_prepare   once per image per step: base assignment of every pixel under the current palette as a
-//                      global entry index (gi), and for pixels of the affected tiles the excluded-entry
-//                      minimum (key, index).
+//                      global entry index (gi), the runner-up's index and both keys.
 //   k_assign_pyr       once per candidate: one distance per affected pixel -> gi map of the candidate, fused
-//                      with the coarse scales (>= 1) of its XYB pyramid, which need every pixel anyway.
+//                      with the coarse scales (>= 1) of its XYB pyramid, which need every pixel anyway.  The replaced
+//                      entry is read per evaluation (CandEntry::slot), so one launch can hold several entries' candidates.
 //
 // Results are identical to running the full S-entry search per candidate (tests compare both paths with
 // the oracle).  RGB keys are the int32 red-mean key; Lab keys are the f32 CIEDE2000 distances (bit pattern
@@ -24,7 +27,7 @@ namespace snes {
 
 // grid = (64, nimg), block 256, 4 horizontally adjacent pixels per thread
 template <bool LAB>
-__global__ void __launch_bounds__(256) k_assign_prepare(const ImgDev *imgs, int S, int CS, int ovr) {
+__global__ void __launch_bounds__(256) k_assign_prepare(const ImgDev *imgs, int S, int CS) {
     __shared__ uchar4 pal[MAX_ENTRIES];
     __shared__ float4 pal_lab[LAB ? MAX_ENTRIES : 1];
     const ImgDev im = imgs[blockIdx.y];
@@ -36,56 +39,57 @@ __global__ void __launch_bounds__(256) k_assign_prepare(const ImgDev *imgs, int 
     __syncthreads();
     const int q = blockIdx.x * 256 + tid, px0 = q * 4, y = px0 >> 8, x = px0 & 255;
     const int sub = im.tile_pal[(y >> 3) * 32 + (x >> 3)] * S;
-    const int psub = (ovr / S) * S, oloc = ovr - psub;
-    const bool affected = sub == psub;
     const uint4 v = __ldg(reinterpret_cast<const uint4 *>(im.rgba) + q);
     const uint32_t pix[4] = {v.x, v.y, v.z, v.w};
-    uint32_t gi4 = 0, ei4 = 0;
-    int ek[4];
+    uint32_t gi4 = 0, si4 = 0;
+    int2 kk[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int r = pix[k] & 255, g = (pix[k] >> 8) & 255, b = (pix[k] >> 16) & 255, a = pix[k] >> 24;
-        int bi = 0, xi = 0;
-        int xkey;
+        // one ascending pass keeps (best, runner-up) as first minima: a new best demotes the old best, which has the lowest
+        // index among the entries of its key seen so far
+        int bi = 0, si = 0xFF;
         if (LAB) {
             const float4 t = __ldg(reinterpret_cast<const float4 *>(im.lab) + px0 + k);
-            float best = __int_as_float(0x7f800000), xbest = __int_as_float(0x7f800000);
+            float best = __int_as_float(0x7f800000), sec = __int_as_float(0x7f800000);
             for (int j = 0; j < S; j++) {
                 const float4 c = pal_lab[sub + j];
                 const float d = ciede2000(c.x, c.y, c.z, t.x, t.y, t.z);
                 if (d < best) {
+                    sec = best;
+                    si = j == 0 ? 0xFF : bi;
                     best = d;
                     bi = j;
-                }
-                if (j != oloc && d < xbest) {
-                    xbest = d;
-                    xi = j;
+                } else if (d < sec) {
+                    sec = d;
+                    si = j;
                 }
             }
-            xkey = __float_as_int(xbest);
+            kk[k] = make_int2(__float_as_int(best), __float_as_int(sec));
         } else {
-            int best = 0x7fffffff, xbest = 0x7fffffff;
+            int best = 0x7fffffff, sec = 0x7fffffff;
             for (int j = 0; j < S; j++) {
                 const uchar4 c = pal[sub + j];
                 const int key = redmean_key(c.x, c.y, c.z, r, g, b);
                 if (key < best) {
+                    sec = best;
+                    si = j == 0 ? 0xFF : bi;
                     best = key;
                     bi = j;
-                }
-                if (j != oloc && key < xbest) {
-                    xbest = key;
-                    xi = j;
+                } else if (key < sec) {
+                    sec = key;
+                    si = j;
                 }
             }
-            xkey = xbest;
+            kk[k] = make_int2(best, sec);
         }
         gi4 |= (uint32_t)(a > 0 ? sub + bi : GI_BLACK) << (8 * k);
-        ei4 |= (uint32_t)((affected && a > 0) ? xi : 0xFF) << (8 * k);   // 0xFF: this pixel cannot change
-        ek[k] = xkey;
+        si4 |= (uint32_t)si << (8 * k);
     }
     reinterpret_cast<uint32_t *>(im.base_gi)[q] = gi4;
-    reinterpret_cast<uint32_t *>(im.excl_idx)[q] = ei4;
-    if (affected) reinterpret_cast<int4 *>(im.excl_key)[q] = make_int4(ek[0], ek[1], ek[2], ek[3]);
+    reinterpret_cast<uint32_t *>(im.sec_idx)[q] = si4;
+    reinterpret_cast<int4 *>(im.keys)[2 * q] = make_int4(kk[0].x, kk[0].y, kk[1].x, kk[1].y);
+    reinterpret_cast<int4 *>(im.keys)[2 * q + 1] = make_int4(kk[2].x, kk[2].y, kk[3].x, kk[3].y);
 }
 
 // k_assign_pyr: grid = (4, evaluations of the chunk), block 256; a CTA owns one 128x128 quadrant.
@@ -107,7 +111,7 @@ constexpr int PYR_MAXJOBS = 1020;   // a multiple of the 5 pixels a block queues
 // per SM pay (0.67 -> 0.59 ms per 4096 evaluations); the CIEDE2000 and full-pyramid modes are faster with their registers
 template <int MODE>
 __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) k_assign_pyr(const ImgDev *imgs, const CandEntry *cents, int ncand, int e0, int S, int CS,
-                                                    int ovr, uint8_t *maps, float *xyb_rm_base, const float *base_xyb) {
+                                                    int has_ovr, uint8_t *maps, float *xyb_rm_base, const float *base_xyb) {
     __shared__ float s_lin[MAX_ENTRIES + 1][3];
     __shared__ float4 s_jobs[(MODE == 2) ? 1 : PYR_MAXJOBS];   // linear RGB + output offset of a queued pixel
     __shared__ int s_njobs;
@@ -120,14 +124,19 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) k_assign_pyr(const Img
     float *rm = xyb_rm_base + (size_t)e * EVAL_XYB_FLOATS;
     uint8_t *map = maps + (size_t)e * NPIX;
     const CandEntry ce = cents[ea];
+    const int ovr = has_ovr >= 0 ? ce.slot : -1;   // the entry this evaluation replaces
     for (int j = tid; j < CS; j += 256)
         for (int c = 0; c < 3; c++) s_lin[j][c] = (j == ovr) ? ce.lin[c] : im.tables->lin[j][c];
     if (tid < 3) {
         s_lin[BLACK][tid] = im.tables->lin[BLACK][tid];
         s_lin[GI_BLACK][tid] = im.tables->lin[BLACK][tid];   // C*S <= 255 on this path: slot 255 is free
     }
-    const int psub = (ovr / S) * S, oloc = ovr - psub;
+    const int psub = ovr >= 0 ? (ovr / S) * S : 0, oloc = ovr - psub;
     const int cr = ce.rgb8.x, cg = ce.rgb8.y, cb = ce.rgb8.z;
+    // bytes of a gi word that lie in the replaced entry's subpalette [psub, psub + S): the pixels this candidate can change
+    // (GI_BLACK = 255 is never in range: C*S <= 255 on this path)
+    const uint32_t lo4 = (uint32_t)psub * 0x01010101u, hi4 = (uint32_t)(psub + S) * 0x01010101u;
+    auto in_sub = [&](uint32_t g) { return __vcmpgeu4(g, lo4) & __vcmpltu4(g, hi4); };
     const float *base = (MODE != 2 && base_xyb) ? base_xyb + (size_t)img * EVAL_XYB_FLOATS : nullptr;
     const uint32_t ovr_rep = (uint32_t)ovr * 0x01010101u;
     if (tid == 0) s_njobs = 0;
@@ -148,24 +157,35 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) k_assign_pyr(const Img
     for (int it = 0; it < 4; it++) {
         const int bx = tid & 31, by = it * 8 + (tid >> 5);   // block inside the quadrant
         const int x0 = qx0 + 4 * bx, y0 = qy0 + 4 * by;
-        uint32_t g4[4], e4[4];
+        uint32_t g4[4], a4[4];   // gi words of the block's rows; a4: 0xFF in the bytes of pixels the candidate can change
 #pragma unroll
         for (int r = 0; r < 4; r++) {
             const int px = (y0 + r) * W + x0;
             if (MODE == 2) {
                 g4[r] = __ldg(reinterpret_cast<const uint32_t *>(map + px));
-                e4[r] = 0xffffffffu;
+                a4[r] = 0u;
             } else {
                 g4[r] = __ldg(reinterpret_cast<const uint32_t *>(im.base_gi + px));
-                e4[r] = __ldg(reinterpret_cast<const uint32_t *>(im.excl_idx + px));
+                a4[r] = in_sub(g4[r]);
             }
         }
+        // (best, runner-up) of pixel px against the candidate's own distance: the first minimum over the other entries is the
+        // best unless the best IS the replaced entry, then the runner-up
+        auto others = [&](int px, int bi, int &xi, int &xkey) {
+            const int2 kk = __ldg(im.keys + px);
+            xi = bi;
+            xkey = kk.x;
+            if (bi == oloc) {
+                xi = im.sec_idx[px];
+                xkey = kk.y;
+            }
+        };
         // MODE 1: CIEDE2000 is expensive and only ~1/C of the blocks are affected, so the warp pools them: two affected
         // blocks at a time, one pixel per lane, and the 16 decisions of a block return to its owner through a ballot
         uint32_t takebits = 0;
         if (MODE == 1) {
             const int lane = tid & 31;
-            const bool aff = (e4[0] & e4[1] & e4[2] & e4[3]) != 0xffffffffu;
+            const bool aff = (a4[0] | a4[1] | a4[2] | a4[3]) != 0u;
             unsigned mask = __ballot_sync(0xffffffffu, aff);
             while (mask) {
                 const int sa = __ffs(mask) - 1;
@@ -176,16 +196,18 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) k_assign_pyr(const Img
                 const int src = lane < 16 ? sa : sb;
                 const int pix = lane & 15, r = pix >> 2, c = pix & 3;
                 const int sx0 = __shfl_sync(0xffffffffu, x0, src), sy0 = __shfl_sync(0xffffffffu, y0, src);
-                const uint32_t w0 = __shfl_sync(0xffffffffu, e4[0], src), w1 = __shfl_sync(0xffffffffu, e4[1], src);
-                const uint32_t w2 = __shfl_sync(0xffffffffu, e4[2], src), w3 = __shfl_sync(0xffffffffu, e4[3], src);
+                const uint32_t w0 = __shfl_sync(0xffffffffu, g4[0], src), w1 = __shfl_sync(0xffffffffu, g4[1], src);
+                const uint32_t w2 = __shfl_sync(0xffffffffu, g4[2], src), w3 = __shfl_sync(0xffffffffu, g4[3], src);
                 const uint32_t w = r == 0 ? w0 : (r == 1 ? w1 : (r == 2 ? w2 : w3));
-                const int xi = (w >> (8 * c)) & 255;
+                const int gi = (w >> (8 * c)) & 255;
                 bool take = false;
-                if (xi != 0xFF && (lane < 16 || hasb)) {
+                if (gi >= psub && gi < psub + S && (lane < 16 || hasb)) {
                     const int px = (sy0 + r) * W + sx0 + c;
                     const float4 t = __ldg(reinterpret_cast<const float4 *>(im.lab) + px);
                     const float d = ciede2000(ce.lab[0], ce.lab[1], ce.lab[2], t.x, t.y, t.z);
-                    const float xb = __int_as_float(__ldg(im.excl_key + px));
+                    int xi, xkey;
+                    others(px, gi - psub, xi, xkey);
+                    const float xb = __int_as_float(xkey);
                     take = d < xb || (d == xb && oloc < xi);
                 }
                 const unsigned tb = __ballot_sync(0xffffffffu, take);
@@ -199,19 +221,19 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) k_assign_pyr(const Img
 #pragma unroll
         for (int r = 0; r < 4; r++) {
             uint32_t out4 = g4[r];
-            if (MODE != 2 && e4[r] != 0xffffffffu) {
+            if (MODE != 2 && a4[r] != 0u) {
                 out4 = 0;
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
                     int gi = (g4[r] >> (8 * c)) & 255;
-                    const int xi = (e4[r] >> (8 * c)) & 255;
-                    if (xi != 0xFF) {   // affected tile, opaque pixel: candidate entry vs the best of the others
+                    if ((a4[r] >> (8 * c)) & 1u) {   // affected tile, opaque pixel: candidate entry vs the best of the others
+                        const int px = (y0 + r) * W + x0 + c;
+                        int xi, xkey;
+                        others(px, gi - psub, xi, xkey);
                         bool take;
                         if (MODE == 1) {
                             take = (takebits >> (4 * r + c)) & 1;
                         } else {
-                            const int px = (y0 + r) * W + x0 + c;
-                            const int xkey = __ldg(im.excl_key + px);
                             const uchar4 p = __ldg(im.rgba + px);
                             const int key = redmean_key(cr, cg, cb, p.x, p.y, p.z);
                             take = key < xkey || (key == xkey && oloc < xi);

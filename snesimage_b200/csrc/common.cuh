@@ -36,13 +36,16 @@ struct PalTables {
     float lab[MAX_ENTRIES][4];      // Lab<D65,f32> of rgb8 (perceptual mode)
 };
 
-// The one palette entry a candidate replaces.
+// The one palette entry a candidate replaces: its colour in every form the kernels need, and WHICH entry it replaces
+// (slot = palette * S + index).  The slot travels with the evaluation, so one launch can carry candidates of several
+// entries (a whole sweep, or the speculated next iterations of one picture).
 struct CandEntry {
     float lin[3];
     float xyb[3];
     uchar4 rgb8;
     float lab[3];
-    uint32_t pad[2];
+    int32_t slot;
+    uint32_t pad;
 };
 
 // Device view of one OptimizedImage.
@@ -60,10 +63,10 @@ struct ImgDev {
     double *cur_err;          // error() of the current state
     const float *lab;         // per-pixel Lab of the original (perceptual mode), [NPIX][4]
     const uint8_t *alpha;     // alpha channel of the original, [NPIX]
-    // per-step scratch of the no-dither candidate path (assign_delta.cuh)
+    // per-step scratch of the no-dither candidate path (assign_delta.cuh), independent of the entry a candidate replaces
     uint8_t *base_gi;         // [NPIX] assignment under the current palette as global entry index (GI_BLACK: transparent)
-    uint8_t *excl_idx;        // [NPIX] best entry other than the replaced one, 0xFF where the pixel cannot change
-    int *excl_key;            // [NPIX] its key (int32 red-mean key, or f32 CIEDE2000 bits)
+    uint8_t *sec_idx;         // [NPIX] runner-up: first minimum over the entries other than the pixel's best (0xFF: S == 1)
+    int2 *keys;               // [NPIX] (key of the best, key of the runner-up): int32 red-mean keys, or f32 CIEDE2000 bits
 };
 
 // A tile-reassignment candidate: tile `tile` (tile_y * 32 + tile_x) bound to subpalette `sub` instead of

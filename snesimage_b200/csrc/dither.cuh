@@ -5,7 +5,11 @@
 // (x-1, y) and on (x-1..x+1, y-1): it can run at wavefront step t = x + 2y, 766 steps per image with
 // at most 128 rows busy.  Thread y owns row y; at step t it handles x = t - 2y, keeps the error of
 // its previous pixel in registers (the E term) and a sliding window of the three errors of the row
-// above, which arrive one per step through a double-buffered shared-memory mailbox.
+// above, which arrive one per step from the thread above: by warp shuffle inside a warp, through a small
+// shared-memory ring with publish / consume counters between warps (DITHER_SHFL, the default), so that no block
+// barrier is left in the 766-step loop and the four warps may drift apart by up to DITHER_RING steps.  The previous
+// hand-over -- a double-buffered mailbox for all 128 threads and one __syncthreads() per step -- is kept under
+// DITHER_SHFL=0 for A/B runs.
 //
 // Bit-exactness: the accumulated error of a pixel is built in the reference's += order, i.e. the
 // raster order of the contributing pixels -- SE term from (x-1,y-1), S from (x,y-1), SW from
@@ -19,6 +23,10 @@
 namespace snes {
 
 constexpr int DITHER_THREADS = 128;
+#ifndef DITHER_SHFL
+#define DITHER_SHFL 1
+#endif
+constexpr int DITHER_RING = 16;      // steps a producing warp may run ahead of the warp that consumes its last row
 #ifndef DITHER_MIN_CTAS
 #define DITHER_MIN_CTAS 6   // 80 registers per thread (ms per 4096 evaluations at 8x15: 8 CTAs = 64 registers 5.75, 7 = 72: 5.05, 6 = 80: 4.62)
 #endif
@@ -30,7 +38,7 @@ constexpr int DITHER_THREADS = 128;
 // of thread i - 1 (thread 127 for the first pixel of row 128), so the mailbox is indexed by thread.
 template <bool LAB>
 __global__ void __launch_bounds__(DITHER_THREADS, DITHER_MIN_CTAS) k_assign_dither(const ImgDev *imgs, const CandEntry *cents, int ncand, int e0, int S,
-                                                                  int CS, int ovr, uint8_t *maps, int to_image, int gi_fmt,
+                                                                  int CS, int has_ovr, uint8_t *maps, int to_image, int gi_fmt,
                                                                   const TileMove *moves /* per evaluation, or null */) {
     __shared__ int4 pal[MAX_ENTRIES];  // r, g, b of as_rgba(entry), 1024 + r
     // red-mean key of entry (R, G, B) against target (r, g, b) with the terms that depend on the target alone dropped
@@ -45,9 +53,17 @@ __global__ void __launch_bounds__(DITHER_THREADS, DITHER_MIN_CTAS) k_assign_dith
     __shared__ int2 kc1[LAB ? 1 : MAX_ENTRIES];  // C1, 2B
     __shared__ float4 pal_lab[LAB ? MAX_ENTRIES : 1];
     __shared__ uint8_t s_tp[NTILES];   // tile_palettes * S
+#if DITHER_SHFL
+    // hand-over between warps: thread 32b+31 publishes its damped error of every step into ring[b], thread (32b+32) % 128
+    // consumes it one step later.  published[b] / consumed[b] count the values written / read (value of step s in slot s % RING).
+    __shared__ double ring[DITHER_THREADS / 32][DITHER_RING][3];
+    __shared__ int published[DITHER_THREADS / 32], consumed[DITHER_THREADS / 32];
+#else
     __shared__ double mail[2][3][DITHER_THREADS];  // [buffer][channel][thread]: conflict-free 8-byte accesses
+#endif
     const int e = blockIdx.x, ea = e0 + e, img = ea / ncand, i = threadIdx.x;
     const ImgDev im = imgs[img];
+    const int ovr = has_ovr >= 0 ? cents[ea].slot : -1;   // the entry this evaluation replaces (per evaluation: CandEntry::slot)
     for (int j = i; j < CS; j += DITHER_THREADS) {
         const uchar4 c = (j == ovr) ? cents[ea].rgb8 : im.tables->rgb8[j];
         pal[j] = make_int4(c.x, c.y, c.z, 1024 + c.x);
@@ -63,7 +79,11 @@ __global__ void __launch_bounds__(DITHER_THREADS, DITHER_MIN_CTAS) k_assign_dith
     }
     for (int j = i; j < NTILES; j += DITHER_THREADS)
         s_tp[j] = (uint8_t)(((moves && moves[ea].tile == j) ? moves[ea].sub : im.tile_pal[j]) * S);
+#if DITHER_SHFL
+    if (i < DITHER_THREADS / 32) published[i] = consumed[i] = 0;
+#else
     for (int c = 0; c < 3; c++) mail[0][c][i] = mail[1][c][i] = 0.0;
+#endif
     __syncthreads();
 
     const double w_e = 7.0 / 16.0, w_sw = 3.0 / 16.0, w_s = 5.0 / 16.0, w_se = 1.0 / 16.0, damp = 0.8;
@@ -75,11 +95,34 @@ __global__ void __launch_bounds__(DITHER_THREADS, DITHER_MIN_CTAS) k_assign_dith
     // four source pixels at a time, requested four steps before their first use
     uint4 nextq = __ldg(reinterpret_cast<const uint4 *>(im.rgba + i * W));
     uint4 curq = nextq;
+#if DITHER_SHFL
+    const int lane = i & 31, wid = i >> 5, b_in = (wid + DITHER_THREADS / 32 - 1) & (DITHER_THREADS / 32 - 1);
+    volatile int *v_pub = published, *v_con = consumed;
+    (void)up;
+#else
     const double *mrd = &mail[1][0][up];  // read side of step t: buffer (t - 1) & 1
     double *mwr = &mail[0][0][i];         // write side of step t: buffer t & 1
+#endif
 
     for (int t = 0; t < W + 2 * (H - 1); t++) {
         const int tau = t - 2 * i;
+#if DITHER_SHFL
+        // the thread above computed pixel x+1 of its row in the previous step: its damped error is still in its `ee`
+        double upv[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) upv[c] = __shfl_up_sync(0xffffffffu, ee[c], 1);
+        if (lane == 0 && t > 0) {   // ... unless it sits in another warp: take the value it published for step t - 1
+            for (int spin = 0; v_pub[b_in] < t; spin++)
+                if (spin > (1 << 24)) __trap();   // a lost hand-over must not hang the GPU
+            __threadfence_block();
+            const double *slot = ring[b_in][(t - 1) & (DITHER_RING - 1)];
+            upv[0] = slot[0];
+            upv[1] = slot[1];
+            upv[2] = slot[2];
+            __threadfence_block();
+            v_con[b_in] = t;
+        }
+#endif
         if (tau >= -1 && tau < 2 * W) {
             // the row above published its pixel x+1 in the previous step (for x = 255 this is already pixel 0 of the row
             // above the thread's second row; the x+1 term of pixel 255 is weighted out below).  Row 0 has no row above:
@@ -89,7 +132,11 @@ __global__ void __launch_bounds__(DITHER_THREADS, DITHER_MIN_CTAS) k_assign_dith
             for (int c = 0; c < 3; c++) {
                 ea_[c] = eb[c];
                 eb[c] = ec[c];
+#if DITHER_SHFL
+                ec[c] = has_up ? upv[c] : 0.0;
+#else
                 ec[c] = has_up ? mrd[c * DITHER_THREADS] : 0.0;
+#endif
             }
         }
         if (tau >= 0 && tau < 2 * W) {
@@ -174,20 +221,35 @@ __global__ void __launch_bounds__(DITHER_THREADS, DITHER_MIN_CTAS) k_assign_dith
                 ee[2] = __dmul_rn(err[2], damp);
                 bi = 0;
             }
+#if !DITHER_SHFL
             mwr[0] = ee[0];
             mwr[DITHER_THREADS] = ee[1];
             mwr[2 * DITHER_THREADS] = ee[2];
+#endif
             packed |= (uint32_t)(gi_fmt ? (opaque ? sub + bi : GI_BLACK) : bi) << (8 * (x & 3));
             if ((x & 3) == 3) {
                 *reinterpret_cast<uint32_t *>(outb + (i + second * DITHER_THREADS) * W + (x & ~3)) = packed;
                 packed = 0;
             }
         }
+#if DITHER_SHFL
+        if (lane == 31) {   // publish this step's value for the first thread of the next warp
+            for (int spin = 0; t - v_con[wid] >= DITHER_RING; spin++)   // slot t % RING still holds an unread value
+                if (spin > (1 << 24)) __trap();
+            double *slot = ring[wid][t & (DITHER_RING - 1)];
+            slot[0] = ee[0];
+            slot[1] = ee[1];
+            slot[2] = ee[2];
+            __threadfence_block();
+            v_pub[wid] = t + 1;
+        }
+#else
         // swap the mailbox buffers for the next step
         const double *nr = mwr - i + up;
         mwr = const_cast<double *>(mrd) - up + i;
         mrd = nr;
         __syncthreads();
+#endif
     }
 }
 

@@ -32,8 +32,11 @@ __device__ __forceinline__ void fill_entry(uint8_t r5, uint8_t g5, uint8_t b5, u
 // boundary) is clamped to 32 for the tables and raises *fault, which the next snes_ctx_synchronize() reports.
 // Evaluation e = (image e / ncand, candidate e % ncand) takes colour cand[(image * cand_stride + cand_lo + candidate)]:
 // a rank evaluating the slice [cand_lo, cand_lo + ncand) of a list of cand_stride candidates per image reads it in place.
+// The entry evaluation (j, k) replaces is slots[k] when a per-candidate slot list is given (one launch holding the
+// candidates of several entries), else `slot` for all of them.
 __global__ void __launch_bounds__(256) k_tables(const ImgDev *imgs, int nimg, int CS, const uint8_t *cand, int E, int ncand,
-                                                int cand_stride, int cand_lo, CandEntry *cents,
+                                                int cand_stride, int cand_lo, int slot, const int *slots /* [ncand] per-candidate, or null */,
+                                                CandEntry *cents,
                                                 const float4 *labtab /* null unless perceptual */, int *fault) {
     const int tid = threadIdx.x;
     if ((int)blockIdx.x < nimg) {
@@ -83,7 +86,8 @@ __global__ void __launch_bounds__(256) k_tables(const ImgDev *imgs, int nimg, in
                 ce.lab[1] = l.y;
                 ce.lab[2] = l.z;
             }
-            ce.pad[0] = ce.pad[1] = 0;
+            ce.slot = slots ? slots[e % ncand] : slot;
+            ce.pad = 0;
             cents[e] = ce;
         }
     }
@@ -99,11 +103,12 @@ __global__ void __launch_bounds__(256) k_tables(const ImgDev *imgs, int nimg, in
 // gi_fmt != 0 (scratch maps of the fused scorer): each byte is the global entry index tile_sub*S + index, or
 // GI_BLACK for a transparent pixel, so the scorer needs neither tile_palettes nor alpha to render the pixel.
 __global__ void __launch_bounds__(256) k_assign_rgb(const ImgDev *imgs, const CandEntry *cents, int ncand, int e0, int S,
-                                                    int CS, int ovr, uint8_t *maps, int to_image, int gi_fmt,
+                                                    int CS, int has_ovr, uint8_t *maps, int to_image, int gi_fmt,
                                                     const TileMove *moves /* per evaluation, or null */) {
     __shared__ uchar4 pal[MAX_ENTRIES];
     const int e = blockIdx.y, ea = e0 + e, img = ea / ncand, tid = threadIdx.x;
     const ImgDev im = imgs[img];
+    const int ovr = has_ovr >= 0 ? cents[ea].slot : -1;   // the entry this evaluation replaces (per evaluation: CandEntry::slot)
     for (int j = tid; j < CS; j += 256) pal[j] = (j == ovr) ? cents[ea].rgb8 : im.tables->rgb8[j];
     __syncthreads();
     const int q = blockIdx.x * 256 + tid;  // quad-of-4 index
@@ -143,7 +148,7 @@ __global__ void __launch_bounds__(256) k_assign_rgb(const ImgDev *imgs, const Ca
 // ------------------------------------------------------------------------------------------------
 template <bool SRC>
 __global__ void __launch_bounds__(256) k_pyramid(const ImgDev *imgs, const CandEntry *cents, int ncand, int e0, int S,
-                                                 int CS, int ovr, const uint8_t *maps, int from_image,
+                                                 int CS, int has_ovr, const uint8_t *maps, int from_image,
                                                  float *xyb_rm_base, int gi_fmt) {
     // SRC: every scale in both layouts (the column-major copy feeds k_blur_h); candidates: only the row-major planes
     // of scales >= 1 (the scorer renders scale 0 itself from the palette_map)
@@ -160,6 +165,7 @@ __global__ void __launch_bounds__(256) k_pyramid(const ImgDev *imgs, const CandE
     // from_image: 1 = the image's own palette_map, 2 = its prepared base assignment (gi format, assign_delta.cuh)
     const uint8_t *map = SRC ? nullptr : (from_image == 2 ? im.base_gi : (from_image ? im.map : maps + (size_t)e * NPIX));
     if (!SRC) {
+        const int ovr = has_ovr >= 0 ? cents[ea].slot : -1;   // the entry this evaluation replaces
         for (int j = tid; j < CS; j += 256) {
             const bool o = (j == ovr);
             for (int c = 0; c < 3; c++) {
@@ -496,18 +502,82 @@ __global__ void k_apply_tile_move(const ImgDev *imgs, int nimg, const TileMove *
     if (applied) applied[j] = took;
 }
 
+// The accept step of `nsteps` consecutive optimiser iterations of an image evaluated against ONE state (speculation: the
+// reference runs them one after the other, lib.rs:889-933, and an iteration that finds nothing better leaves the state
+// as it was, so the next iteration's evaluations against the old state are exactly the reference's).  best[j][s] is the
+// first minimum of step s's candidates.  Steps are taken in order; the first whose best beats the image's current error
+// (lib.rs:216-219; force: NES, lib.rs:250) is applied and ends the run: consumed[j] = its number + 1 (nsteps if none),
+// chosen[j] = the accepted evaluation's index among the image's nsteps * ncand evaluations, or -1.
+__global__ void k_apply_first_accept(const ImgDev *imgs, int nimg, const int *step_slot, int nsteps, const uint8_t *cand, int ncand,
+                                     const Best *best, int force, int *consumed, int *chosen) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nimg) return;
+    const ImgDev im = imgs[j];
+    int used = nsteps, pick = -1;
+    for (int s = 0; s < nsteps; s++) {
+        const Best b = best[(size_t)j * nsteps + s];
+        if (b.idx < 0 || b.idx >= ncand) continue;
+        const uint8_t *c = cand + (((size_t)j * nsteps + s) * ncand + b.idx) * 3;
+        if (c[0] > 32 || c[1] > 32 || c[2] > 32) continue;
+        if (force || b.err < *im.cur_err) {
+            const int slot = step_slot[s];
+            im.palette[3 * slot] = c[0];
+            im.palette[3 * slot + 1] = c[1];
+            im.palette[3 * slot + 2] = c[2];
+            *im.cur_err = b.err;
+            used = s + 1;
+            pick = s * ncand + b.idx;
+            break;
+        }
+    }
+    consumed[j] = used;
+    chosen[j] = pick;
+}
+
+// optimize() after an accepted candidate without running it again: the accepted evaluation's assignment is still in the
+// scratch maps (gi format: tile_sub * S + index, GI_BLACK for a transparent pixel) and IS optimize() of the new state
+// (lib.rs:236-237 recompute what lib.rs:212 computed for that candidate).  grid = (64, nimg), block 256, 4 pixels per thread.
+__global__ void __launch_bounds__(256) k_adopt_map(const ImgDev *imgs, const int *chosen, const uint8_t *maps, int ncand_total, int S) {
+    const int j = blockIdx.y, pick = chosen[j];
+    if (pick < 0) return;
+    const ImgDev im = imgs[j];
+    const int q = blockIdx.x * 256 + threadIdx.x, px0 = q * 4, y = px0 >> 8, x = px0 & 255;
+    const uint32_t g = reinterpret_cast<const uint32_t *>(maps + ((size_t)j * ncand_total + pick) * NPIX)[q];
+    const int sub = im.tile_pal[(y >> 3) * 32 + (x >> 3)] * S;
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int gi = (g >> (8 * k)) & 255;
+        out |= (uint32_t)(gi == GI_BLACK ? 0 : gi - sub) << (8 * k);
+    }
+    reinterpret_cast<uint32_t *>(im.map)[q] = out;
+}
+
 // current error of each image := scores[j]  (after an error() pass over the images themselves)
 __global__ void k_store_cur_err(const ImgDev *imgs, int nimg, const double *scores) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < nimg) *imgs[j].cur_err = scores[j];
 }
 
+// out[j] := current error of image j
+__global__ void k_load_cur_err(const ImgDev *imgs, int nimg, double *out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nimg) out[j] = *imgs[j].cur_err;
+}
+
 // candidate lists built on the device: the 56 NES colours (lib.rs:252-253) or the 32 values of one
 // channel of the current entry (lib.rs:296-297).  grid = nimg, block 64.
-__global__ void k_make_cands(const ImgDev *imgs, int slot, int channel /* -1: NES */, uint8_t *cand, int ncand) {
-    const int j = blockIdx.x, k = threadIdx.x;
+// With several steps per image (grid = (nimg, nsteps)) step s uses entry step_slot[s] and channel step_channel[s]; the lists
+// of an image follow each other.
+__global__ void k_make_cands(const ImgDev *imgs, int slot, int channel /* -1: NES */, uint8_t *cand, int ncand,
+                             const int *step_slot = nullptr, const int *step_channel = nullptr) {
+    const int j = blockIdx.x, k = threadIdx.x, s = blockIdx.y;
     if (k >= ncand) return;
-    uint8_t *o = cand + ((size_t)j * ncand + k) * 3;
+    if (step_slot) {
+        slot = step_slot[s];
+        channel = step_channel[s];
+    }
+    uint8_t *o = cand + (((size_t)j * gridDim.y + s) * ncand + k) * 3;
     if (channel < 0) {
         o[0] = c_nes[k][0];
         o[1] = c_nes[k][1];

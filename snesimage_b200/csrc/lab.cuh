@@ -158,11 +158,12 @@ __global__ void __launch_bounds__(256) k_image_lab(const uchar4 *rgba, float4 *l
 // k_assign_lab: optimize() (lib.rs:425-501) without dithering, CIEDE2000 metric.  Same launch shape
 // and outputs as k_assign_rgb: grid (64, E), block 256, 4 pixels per thread.
 __global__ void __launch_bounds__(256) k_assign_lab(const ImgDev *imgs, const CandEntry *cents, int ncand, int e0, int S,
-                                                    int CS, int ovr, uint8_t *maps, int to_image, int gi_fmt,
+                                                    int CS, int has_ovr, uint8_t *maps, int to_image, int gi_fmt,
                                                     const TileMove *moves /* per evaluation, or null */) {
     __shared__ float4 pal[MAX_ENTRIES];
     const int e = blockIdx.y, ea = e0 + e, img = ea / ncand, tid = threadIdx.x;
     const ImgDev im = imgs[img];
+    const int ovr = has_ovr >= 0 ? cents[ea].slot : -1;   // the entry this evaluation replaces (per evaluation: CandEntry::slot)
     for (int j = tid; j < CS; j += 256) {
         const float *l = (j == ovr) ? cents[ea].lab : im.tables->lab[j];
         pal[j] = make_float4(l[0], l[1], l[2], 0.0f);

@@ -15,7 +15,8 @@ namespace snes {
 struct FusedArgs {
     const ImgDev *imgs;
     const CandEntry *cents;
-    int ncand, e0, S, CS, ovr;
+    int ncand, e0, S, CS;
+    int ovr;                 // >= 0: every evaluation replaces one palette entry, named by its CandEntry::slot; -1: none
     const uint8_t *maps;     // [chunk][NPIX] palette_maps of the evaluations (ignored when from_image)
     int from_image;
     int gi_fmt;              // maps hold global entry indices (k_assign_* with gi_fmt), not palette_map values

@@ -83,6 +83,10 @@ struct snes_ctx {
     double *self_scores = nullptr;
     std::vector<snes_image *> cached;
 
+    int *d_ints = nullptr;     // small integer scratch of the multi-entry calls: slots, channels, consumed, chosen
+    size_t ints_cap = 0;
+    Best *best_m = nullptr;    // [nimg * nsteps] first minima of a multi-entry call
+    size_t best_m_cap = 0;
     int shard_ncand_all = 0;   // candidates per image of the list snes_batch_step_random_shard_begin left in `cand`
 
     float4 *labtab = nullptr;  // BGR555 -> Lab<D65,f32>
@@ -102,6 +106,7 @@ struct snes_image {
     void *slab = nullptr, *km_slab = nullptr;
     ImgTm tm{};                  // TMA tensor maps over the slab (source pyramid per scale, own palette_map)
     std::vector<uint8_t> alpha;  // host copy of the alpha channel (as_json)
+    bool map_fresh = false;      // palette_map is optimize() of the current palette and tile assignment (no setter since)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -391,6 +396,8 @@ extern "C" void snes_ctx_destroy(snes_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_scratch(ctx);
     cudaFree(ctx->labtab);
+    cudaFree(ctx->d_ints);
+    cudaFree(ctx->best_m);
     cudaFree(ctx->hbuf);
     cudaFree(ctx->d_fault);
     cudaFree(ctx->v3_counter);
@@ -581,6 +588,8 @@ struct EvalPlan {
     int nimg = 0;
     int ncand = 1;                    // evaluations per image
     int ovr = -1;                     // palette slot replaced by the candidate colour, -1: none
+    const int *d_slots = nullptr;     // device [ncand]: candidate k of every image replaces entry d_slots[k] instead of `ovr` (ovr >= 0 still
+                                      // says that the evaluations replace an entry at all)
     const uint8_t *d_cand = nullptr;  // device, required when ovr >= 0: [nimg][cand_stride][3], evaluation (j, k) reads candidate cand_lo + k
     int cand_stride = 0, cand_lo = 0; // candidates per image in d_cand (0: ncand) and the first one this plan evaluates
     bool self = false;                // operate on the images' own palette_map instead of scratch maps
@@ -627,7 +636,7 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
 
     LAUNCH(ctx, "k_tables", k_tables<<<pl.nimg + (pl.ovr >= 0 ? (E + 255) / 256 : 0), 256, 0, st>>>(ctx->d_imgs, pl.nimg, CS, pl.d_cand,
                                                                           pl.ovr >= 0 ? E : 0, pl.ncand, pl.cand_stride ? pl.cand_stride : pl.ncand,
-                                                                          pl.cand_lo, ctx->cents, labtab, ctx->d_fault));
+                                                                          pl.cand_lo, pl.ovr, pl.d_slots, ctx->cents, labtab, ctx->d_fault));
 
     // error() of the images' own state riding in the candidates' scorer launch: its coarse pyramid and partial sums
     // live in their own buffers; the 3 * nimg extra items join the first chunk
@@ -656,9 +665,9 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
     const bool delta = delta_path;
     if (delta) {
         if (cfg.perceptual_palettes)
-            LAUNCH(ctx, "k_assign_prepare<true>", k_assign_prepare<true><<<dim3(64, pl.nimg), 256, 0, st>>>(ctx->d_imgs, S, CS, pl.ovr));
+            LAUNCH(ctx, "k_assign_prepare<true>", k_assign_prepare<true><<<dim3(64, pl.nimg), 256, 0, st>>>(ctx->d_imgs, S, CS));
         else
-            LAUNCH(ctx, "k_assign_prepare<false>", k_assign_prepare<false><<<dim3(64, pl.nimg), 256, 0, st>>>(ctx->d_imgs, S, CS, pl.ovr));
+            LAUNCH(ctx, "k_assign_prepare<false>", k_assign_prepare<false><<<dim3(64, pl.nimg), 256, 0, st>>>(ctx->d_imgs, S, CS));
         // coarse pyramid of the prepared base assignment (current palette, no candidate): k_assign_pyr copies the blocks
         // a candidate leaves unchanged from it
         LAUNCH(ctx, "k_pyramid<false>", k_pyramid<false><<<dim3(16, pl.nimg), 256, 0, st>>>(ctx->d_imgs, ctx->cents, 1, 0, S, CS, -1, nullptr, 2,
@@ -755,7 +764,9 @@ static int batch_optimize(snes_ctx *ctx, snes_image *const *images, int nimg) {
     pl.nimg = nimg;
     pl.self = true;
     pl.do_assign = true;
-    return run_plan(ctx, images[0]->cfg, pl);
+    RET(run_plan(ctx, images[0]->cfg, pl));
+    for (int j = 0; j < nimg; j++) images[j]->map_fresh = true;
+    return SNES_OK;
 }
 
 // error() of every image in the batch (lib.rs:503-548) -> cur_err of each image (and ctx->self_scores)
@@ -808,7 +819,7 @@ extern "C" int snes_image_new(snes_ctx *ctx, const uint8_t *rgba, int width, int
     const size_t o_tab = take(sizeof(PalTables)), o_err = take(sizeof(double));
     const size_t o_lab = take(im->cfg.perceptual_palettes ? sizeof(float4) * NPIX : 0);
     const size_t o_alpha = take(NPIX);
-    const size_t o_bgi = take(NPIX), o_xi = take(NPIX), o_xk = take(sizeof(int) * NPIX);
+    const size_t o_bgi = take(NPIX), o_xi = take(NPIX), o_xk = take(sizeof(int2) * NPIX);
     cudaError_t e = cudaMalloc(&im->slab, off);
     if (e != cudaSuccess) {
         delete im;
@@ -829,8 +840,8 @@ extern "C" int snes_image_new(snes_ctx *ctx, const uint8_t *rgba, int width, int
     im->dev.lab = im->cfg.perceptual_palettes ? (const float *)(b + o_lab) : nullptr;
     im->dev.alpha = (const uint8_t *)(b + o_alpha);
     im->dev.base_gi = (uint8_t *)(b + o_bgi);
-    im->dev.excl_idx = (uint8_t *)(b + o_xi);
-    im->dev.excl_key = (int *)(b + o_xk);
+    im->dev.sec_idx = (uint8_t *)(b + o_xi);
+    im->dev.keys = (int2 *)(b + o_xk);
 
     cudaStream_t st = ctx->stream;
     int rc = SNES_OK;
@@ -1045,6 +1056,7 @@ extern "C" int snes_image_set_palette(snes_image *im, const uint8_t *in) {
     // SnesColor values are 5-bit; 32 can arise from round(v/8) (lib.rs:396-400) and is kept
     for (size_t i = 0; i < n; i++)
         if (in[i] > 32) return fail(SNES_E_INVALID, "snes_image_set_palette: colour component > 32");
+    im->map_fresh = false;
     return h2d(im, im->dev.palette, in, n);
 }
 extern "C" int snes_image_get_tile_palettes(snes_image *im, uint8_t *out) { return d2h(im, out, im ? im->dev.tile_pal : nullptr, NTILES); }
@@ -1052,6 +1064,7 @@ extern "C" int snes_image_set_tile_palettes(snes_image *im, const uint8_t *in) {
     if (!im || !in) return fail(SNES_E_INVALID, "accessor: NULL argument");
     for (int i = 0; i < NTILES; i++)
         if (in[i] >= im->cfg.subpalette_count) return fail(SNES_E_INVALID, "snes_image_set_tile_palettes: index >= subpalette_count");
+    im->map_fresh = false;
     return h2d(im, im->dev.tile_pal, in, NTILES);
 }
 extern "C" int snes_image_get_palette_map(snes_image *im, uint8_t *out) { return d2h(im, out, im ? im->dev.map : nullptr, NPIX); }
@@ -1059,6 +1072,7 @@ extern "C" int snes_image_set_palette_map(snes_image *im, const uint8_t *in) {
     if (!im || !in) return fail(SNES_E_INVALID, "accessor: NULL argument");
     for (int i = 0; i < NPIX; i++)
         if (in[i] >= im->cfg.subpalette_size) return fail(SNES_E_INVALID, "snes_image_set_palette_map: index >= subpalette_size");
+    im->map_fresh = false;
     return h2d(im, im->dev.map, in, NPIX);
 }
 
@@ -1436,6 +1450,142 @@ extern "C" int snes_batch_step_nes(snes_ctx *ctx, snes_image *const *images, int
 extern "C" int snes_batch_step_channel(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index, int channel,
                                        snes_best *best, double *errors_after) {
     return batch_step(ctx, images, nimg, palette, index, 2, channel, nullptr, 0, best, errors_after);
+}
+
+// ---- several palette entries in one launch sequence (TODO.md:33-35) -----------------------------
+// Evaluation (j, s * ncand + k) = image j with entry steps[s] replaced by candidate k of step s.  Every kernel reads the
+// replaced entry per evaluation (CandEntry::slot), and k_assign_prepare's records do not depend on it, so the candidates of
+// a whole sweep -- or of the next few iterations of one picture -- share one k_tables / prepare / assign / score sequence.
+static int ensure_ints(snes_ctx *ctx, size_t n) {
+    if (n <= ctx->ints_cap) return SNES_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_ints);
+    ctx->d_ints = nullptr;
+    ctx->ints_cap = 0;
+    RET(dev_alloc(&ctx->d_ints, n));
+    ctx->ints_cap = n;
+    return SNES_OK;
+}
+static int ensure_best_m(snes_ctx *ctx, size_t n) {
+    if (n <= ctx->best_m_cap) return SNES_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->best_m);
+    ctx->best_m = nullptr;
+    ctx->best_m_cap = 0;
+    RET(dev_alloc(&ctx->best_m, n));
+    ctx->best_m_cap = n;
+    return SNES_OK;
+}
+
+struct MultiLayout {   // offsets into ctx->d_ints
+    int *slots, *step_slot, *step_channel, *consumed, *chosen;
+};
+
+// mode 0: explicit candidates cand[nimg][nsteps][ncand][3] (host); 1: the 56 NES colours; 2: the 32 values of steps[s].channel.
+// Leaves scores in ctx->scores ([nimg][nsteps][ncand]) and the per-step first minima in ctx->best_m ([nimg][nsteps]).
+static int eval_multi(snes_ctx *ctx, snes_image *const *images, int nimg, int mode, const snes_step *steps, int nsteps, const uint8_t *cand,
+                      int &ncand, bool with_error, MultiLayout &lay) {
+    RET(bind_images(ctx, images, nimg));
+    const snes_config cfg = images[0]->cfg;
+    if (!steps || nsteps < 1 || nsteps > 4096) return fail(SNES_E_INVALID, "multi-entry call: need 1..4096 steps");
+    if (mode < 0 || mode > 2) return fail(SNES_E_INVALID, "multi-entry call: mode must be 0 (random), 1 (NES) or 2 (channel)");
+    if (mode == 1) ncand = NES_COUNT;
+    if (mode == 2) ncand = 32;
+    if (mode == 0 && (!cand || ncand < 1)) return fail(SNES_E_INVALID, "no candidates");
+    for (int s = 0; s < nsteps; s++) {
+        RET(check_slot(cfg, steps[s].palette, steps[s].index));
+        if (mode == 2 && (steps[s].channel < 0 || steps[s].channel > 2)) return fail(SNES_E_INVALID, "channel out of range");
+    }
+    const int per_img = nsteps * ncand;
+    const size_t E = (size_t)nimg * per_img;
+    if (mode == 0)
+        for (size_t i = 0; i < E * 3; i++)
+            if (cand[i] > 32) return fail(SNES_E_INVALID, "colour component > 32");
+    RET(ensure_evals(ctx, E));
+    RET(ensure_ints(ctx, (size_t)per_img + 2 * nsteps + 2 * nimg));
+    RET(ensure_best_m(ctx, (size_t)nimg * nsteps));
+    lay.slots = ctx->d_ints;
+    lay.step_slot = lay.slots + per_img;
+    lay.step_channel = lay.step_slot + nsteps;
+    lay.consumed = lay.step_channel + nsteps;
+    lay.chosen = lay.consumed + nimg;
+    std::vector<int> h((size_t)per_img + 2 * nsteps);
+    for (int s = 0; s < nsteps; s++) {
+        const int slot = steps[s].palette * cfg.subpalette_size + steps[s].index;
+        for (int k = 0; k < ncand; k++) h[(size_t)s * ncand + k] = slot;
+        h[(size_t)per_img + s] = slot;
+        h[(size_t)per_img + nsteps + s] = mode == 1 ? -1 : steps[s].channel;
+    }
+    cudaStream_t st = ctx->stream;
+    // (pageable source: the copy is staged before the call returns, so the vector may go out of scope)
+    CK(cudaMemcpyAsync(ctx->d_ints, h.data(), sizeof(int) * h.size(), cudaMemcpyHostToDevice, st));
+    if (mode == 0) CK(cudaMemcpyAsync(ctx->cand, cand, E * 3, cudaMemcpyHostToDevice, st));
+    else LAUNCH(ctx, "k_make_cands", k_make_cands<<<dim3(nimg, nsteps), 64, 0, st>>>(ctx->d_imgs, 0, 0, ctx->cand, ncand, lay.step_slot, lay.step_channel));
+    if (with_error && ctx->fused != 3) RET(batch_error(ctx, images, nimg));
+    EvalPlan pl;
+    pl.nimg = nimg;
+    pl.ncand = per_img;
+    pl.ovr = h[per_img];
+    pl.d_slots = lay.slots;
+    pl.d_cand = ctx->cand;
+    pl.do_assign = pl.do_score = true;
+    pl.d_scores = ctx->scores;
+    pl.with_self_error = with_error && ctx->fused == 3;
+    RET(run_plan(ctx, cfg, pl));
+    LAUNCH(ctx, "k_argmin", k_argmin<<<nimg * nsteps, 128, 0, st>>>(ctx->scores, ncand, 0, ctx->best_m));
+    return SNES_OK;
+}
+
+extern "C" int snes_batch_eval_candidates_multi(snes_ctx *ctx, snes_image *const *images, int nimg, const snes_step *steps, int nsteps,
+                                                const uint8_t *cand, int ncand, double *scores, snes_best *best) {
+    MultiLayout lay;
+    RET(eval_multi(ctx, images, nimg, 0, steps, nsteps, cand, ncand, false, lay));
+    cudaStream_t st = ctx->stream;
+    if (scores) CK(cudaMemcpyAsync(scores, ctx->scores, sizeof(double) * nimg * nsteps * ncand, cudaMemcpyDeviceToHost, st));
+    if (best) CK(cudaMemcpyAsync(best, ctx->best_m, sizeof(Best) * nimg * nsteps, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SNES_OK;
+}
+
+// `nsteps` consecutive iterations of the loop of run() (lib.rs:889-910) for every image of the batch, speculatively: all
+// steps' candidates are evaluated against the current state in one launch sequence, then the steps are taken in order
+// until the first one that accepts a candidate (k_apply_first_accept).  The iterations before it found nothing better, so
+// the state they would have left is the one they were evaluated against: the result is the reference's, iteration by
+// iteration.  The trailing optimize() / error() of each iteration (lib.rs:906-910) recompute what is already known: the
+// accepted evaluation's palette_map is adopted from the scratch maps (k_adopt_map) and its score is the new error.
+static int iterate_multi(snes_ctx *ctx, snes_image *const *images, int nimg, int mode, const snes_step *steps, int nsteps, const uint8_t *cand,
+                         int ncand, int *consumed, double *errors_before, double *errors_after) {
+    MultiLayout lay;
+    if (mode == 1 && nsteps != 1) return fail(SNES_E_INVALID, "NES iterations always replace the entry (lib.rs:250): one step per call");
+    RET(eval_multi(ctx, images, nimg, mode, steps, nsteps, cand, ncand, mode != 1, lay));
+    const snes_config cfg = images[0]->cfg;
+    cudaStream_t st = ctx->stream;
+    const int per_img = nsteps * ncand;
+    // error() of the state the steps were evaluated against (lib.rs:199, 294); NES steps do not compute it (lib.rs:250)
+    if (errors_before && mode != 1) CK(cudaMemcpyAsync(errors_before, ctx->self_scores, sizeof(double) * nimg, cudaMemcpyDeviceToHost, st));
+    LAUNCH(ctx, "k_apply_first_accept", k_apply_first_accept<<<(nimg + 127) / 128, 128, 0, st>>>(ctx->d_imgs, nimg, lay.step_slot, nsteps, ctx->cand, ncand,
+                                                                           ctx->best_m, mode == 1, lay.consumed, lay.chosen));
+    bool fresh = cfg.subpalette_count * cfg.subpalette_size <= 255 && (size_t)nimg * per_img <= (size_t)ctx->chunk;
+    for (int j = 0; j < nimg; j++) fresh = fresh && images[j]->map_fresh;
+    if (fresh) {
+        LAUNCH(ctx, "k_adopt_map", k_adopt_map<<<dim3(64, nimg), 256, 0, st>>>(ctx->d_imgs, lay.chosen, ctx->maps, per_img, cfg.subpalette_size));
+    } else {
+        RET(batch_optimize(ctx, images, nimg));   // stale palette_map, or the scratch maps of the first chunks are gone
+    }
+    if (consumed) CK(cudaMemcpyAsync(consumed, lay.consumed, sizeof(int) * nimg, cudaMemcpyDeviceToHost, st));
+    if (errors_after) {
+        LAUNCH(ctx, "k_load_cur_err", k_load_cur_err<<<(nimg + 127) / 128, 128, 0, st>>>(ctx->d_imgs, nimg, ctx->self_scores));
+        CK(cudaMemcpyAsync(errors_after, ctx->self_scores, sizeof(double) * nimg, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return SNES_OK;
+}
+
+extern "C" int snes_image_iterate(snes_image *im, int mode, const snes_step *steps, int nsteps, const uint8_t *cand, int ncand,
+                                  int *consumed, double *error_before, double *error_after) {
+    if (!im) return fail(SNES_E_INVALID, "image is NULL");
+    snes_image *one[1] = {im};
+    return iterate_multi(im->ctx, one, 1, mode, steps, nsteps, cand, ncand, consumed, error_before, error_after);
 }
 
 extern "C" int snes_image_optimize_palette_entry_random(snes_image *im, int palette, int index, const uint8_t *cand, int ncand) {

@@ -224,15 +224,19 @@ def sweep_random(images: Sequence[engine.OptimizedImage], seed: int, sweep: int,
     C, S, nimg = cfg.subpalette_count, cfg.subpalette_size, len(images)
     base = engine.batch_error(images)
     winners = [[] for _ in range(nimg)]          # per image: (predicted error, subpalette, index, colour)
+    # every entry's candidates in ONE launch sequence (snes_batch_eval_candidates_multi): the kernels read the replaced entry
+    # per evaluation, so the C*S lists share one k_tables / prepare / assign / score pass
+    steps = [(p, i) for p in range(C) for i in range(S)]
+    cand = np.stack([np.stack([synth.candidates(seed * 1000003 + j, sweep * C * S + p * S + i, ncand) for p, i in steps]) for j in range(nimg)])
+    r = engine.batch_eval_candidates_multi(images, steps, cand)
     for p in range(C):
         best_p = [None] * nimg
         for i in range(S):
-            cand = np.stack([synth.candidates(seed * 1000003 + j, sweep * C * S + p * S + i, ncand) for j in range(nimg)])
-            r = engine.batch_eval_candidates(images, p, i, cand, want_scores=False)
+            s = p * S + i
             for j in range(nimg):
-                err, k = float(r["best"]["err"][j]), int(r["best"]["idx"][j])
+                err, k = float(r["best"]["err"][j, s]), int(r["best"]["idx"][j, s])
                 if k >= 0 and err < base[j] and (best_p[j] is None or err < best_p[j][0]):
-                    best_p[j] = (err, p, i, cand[j, k].copy())
+                    best_p[j] = (err, p, i, cand[j, s, k].copy())
         for j in range(nimg):
             if best_p[j] is not None:
                 winners[j].append(best_p[j])
@@ -264,8 +268,14 @@ class HeadlessRunner:
     # recalculate_palettes) -> Optimization; the optimiser only iterates in the last phase (lib.rs:889).
     TILE_ASSIGNMENT, CLUSTERING, OPTIMIZATION = "TileAssignment", "Clustering", "Optimization"
 
-    def __init__(self, ctx: engine.Context, rgba: np.ndarray, config: engine.Config, seed: int = 0, ncand: int = 64):
+    def __init__(self, ctx: engine.Context, rgba: np.ndarray, config: engine.Config, seed: int = 0, ncand: int = 64,
+                 speculate: int = 4):
+        """speculate: how many iterations ahead `iterate(n)` may evaluate in one call (1 = one at a time).  One picture's
+        64 candidates fill a fraction of a B200; the candidates of the next few entries ride along, and are used up to the
+        first iteration that accepts one (snes_image_iterate) -- the trajectory is the reference's either way."""
         self.image = engine.OptimizedImage(ctx, rgba, config)
+        self.speculate = max(1, int(speculate))
+        self.depth = self.speculate
         self.config = config
         self.cursor = Cursor()
         self.seed, self.ncand = seed, ncand
@@ -334,21 +344,34 @@ class HeadlessRunner:
         if self.phase != self.OPTIMIZATION:      # lib.rs:889: the optimiser only runs in the last phase
             return
         im, c = self.image, self.cursor
-        for _ in range(n):
+        done = 0
+        while done < n:
             mode = c.mode(self.config)
-            if mode == "nes":
-                im.optimize_palette_entry_nes(c.palette, c.palette_index)
-            elif mode == "random":
-                im.optimize_palette_entry_random(c.palette, c.palette_index, synth.candidates(self.seed, self.iteration, self.ncand))
-            else:
-                im.optimize_palette_entry_channel(c.palette, c.palette_index, c.channel)
-            im.optimize()                    # lib.rs:906-908
-            error = im.error()               # lib.rs:910
-            if abs(error - self.last_error) > np.finfo(np.float64).eps:
-                self.last_error = error
-                self.log.append(error)
-            c.advance(self.config)
-            self.iteration += 1
+            # the iterations ahead of the cursor that share this one's mode, at most `depth` of them (NES iterations always
+            # replace their entry, lib.rs:250, so nothing can be evaluated ahead of them)
+            ahead = 1 if mode == "nes" else min(self.depth, n - done)
+            steps, cands, look = [], [], Cursor(c.palette, c.palette_index, c.channel, c.step)
+            for k in range(ahead):
+                if look.mode(self.config) != mode:
+                    break
+                steps.append((look.palette, look.palette_index, look.channel))
+                if mode == "random":
+                    cands.append(synth.candidates(self.seed, self.iteration + k, self.ncand))
+                look.advance(self.config)
+            # optimize_palette_entry_* + optimize() + error() (lib.rs:892-910) of `used` iterations in one call
+            used, before, error = im.iterate(mode, steps, np.stack(cands) if cands else None)
+            if self.speculate > 1 and mode != "nes":   # look further ahead while nothing is accepted, less far when the first step was
+                self.depth = min(2 * self.speculate, self.depth * 2) if used == len(steps) and len(steps) == self.depth else (
+                    max(1, self.depth // 2) if used == 1 and len(steps) > 1 else self.depth)
+            # lib.rs:912-915 per iteration: the iterations before the last consumed one ended with the error they started from
+            for e in ([before] if used > 1 else []) + [error]:
+                if abs(e - self.last_error) > np.finfo(np.float64).eps:
+                    self.last_error = e
+                    self.log.append(e)
+            for _ in range(used):
+                c.advance(self.config)
+            self.iteration += used
+            done += used
 
     def write_json(self, path: str):
         with open(path, "w") as f:           # lib.rs:999-1003

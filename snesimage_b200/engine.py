@@ -47,6 +47,11 @@ class Best(C.Structure):
 BEST_DTYPE = np.dtype([("err", "<f8"), ("idx", "<i4"), ("pad", "<i4")])
 
 
+class Step(C.Structure):
+    """snes_step: the palette entry (and channel) one iteration of run() works on."""
+    _fields_ = [("palette", C.c_int32), ("index", C.c_int32), ("channel", C.c_int32), ("reserved", C.c_int32)]
+
+
 class _Config(C.Structure):
     _fields_ = [("subpalette_count", C.c_int32), ("subpalette_size", C.c_int32), ("dither", C.c_uint8),
                 ("perceptual_palettes", C.c_uint8), ("nes", C.c_uint8), ("reserved", C.c_uint8)]
@@ -113,6 +118,8 @@ _SIGNATURES = {
     "snes_batch_step_random_shard_begin": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "snes_batch_step_random_shard_end": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "snes_image_state_checksum": (_i, [_vp, C.POINTER(C.c_uint64)]),
+    "snes_batch_eval_candidates_multi": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp]),
+    "snes_image_iterate": (_i, [_vp, _i, _vp, _i, _vp, _i, C.POINTER(_i), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "snes_batch_apply_best_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "snes_merge_best_dev": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "snes_batch_step_random": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),
@@ -300,6 +307,21 @@ class OptimizedImage:
         _check(self._l.snes_image_optimize_palette_entry_channel(self._h, palette, index, channel),
                "Unable to optimize palette with the channel method")
 
+    def iterate(self, mode: str, steps, cand=None):
+        """`len(steps)` consecutive iterations of run()'s loop (lib.rs:889-910) in one call, speculatively (see
+        snes_image_iterate).  steps: (palette, index[, channel]) tuples; cand (random mode): (len(steps), ncand, 3).
+        Returns (iterations consumed, error() before, error() of the new state); error before is NaN in NES mode."""
+        arr, n = _steps(steps)
+        m = {"random": 0, "nes": 1, "channel": 2}[mode]
+        ncand = 0
+        if m == 0:
+            cand = _u8(cand).reshape(n, -1, 3)
+            ncand = cand.shape[1]
+        used, before, err = _i(0), C.c_double(float("nan")), C.c_double(0.0)
+        _check(self._l.snes_image_iterate(self._h, m, arr, n, _ptr(cand) if m == 0 else None, ncand, C.byref(used), C.byref(before),
+                                          C.byref(err)), "Unable to optimize palette")
+        return int(used.value), float(before.value), float(err.value)
+
     def as_json_string(self) -> str:
         n = _sz(0)
         _check(self._l.snes_image_as_json(self._h, None, 0, C.byref(n)), "as_json")
@@ -418,6 +440,27 @@ def batch_eval_candidates(images: Sequence[OptimizedImage], palette: int, index:
     _check(ctx._l.snes_batch_eval_candidates(ctx._h, _handles(images), nimg, palette, index, _ptr(cand), ncand, _ptr(scores),
                                              _ptr(maps), _ptr(best)), "snes_batch_eval_candidates")
     return {"scores": scores, "maps": maps, "best": best}
+
+
+def _steps(steps):
+    steps = [tuple(s) + (0,) * (3 - len(tuple(s))) for s in steps]
+    arr = (Step * len(steps))(*[Step(int(p), int(i), int(ch), 0) for p, i, ch in steps])
+    return arr, len(steps)
+
+
+def batch_eval_candidates_multi(images: Sequence[OptimizedImage], steps, cand) -> dict:
+    """Candidates of several palette entries against ONE state in one launch sequence.  steps: (palette, index) tuples;
+    cand: (nimg, nsteps, ncand, 3).  Returns scores (nimg, nsteps, ncand) and best (nimg, nsteps)."""
+    ctx = _ctx_of(images)
+    nimg = len(images)
+    arr, n = _steps(steps)
+    cand = _u8(cand).reshape(nimg, n, -1, 3)
+    ncand = cand.shape[2]
+    scores = np.zeros((nimg, n, ncand), np.float64)
+    best = np.zeros((nimg, n), BEST_DTYPE)
+    _check(ctx._l.snes_batch_eval_candidates_multi(ctx._h, _handles(images), nimg, arr, n, _ptr(cand), ncand, _ptr(scores), _ptr(best)),
+           "snes_batch_eval_candidates_multi")
+    return {"scores": scores, "best": best}
 
 
 def batch_step_random(images: Sequence[OptimizedImage], palette: int, index: int, cand, want_errors: bool = False):

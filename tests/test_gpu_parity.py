@@ -444,6 +444,99 @@ def test_sharded_driver_plans_match_single_rank(ctx, nimg, world, mode):
             im.close()
 
 
+def test_sharded_step_host_halves_match_single_call(ctx):
+    """snes_batch_step_random_shard_begin / _end (host buffers, the caller's all-gather in between) on two emulated ranks
+    that slice the candidates of the same images give the state and records of one snes_batch_step_random call."""
+    import torch
+    from snesimage_b200 import driver
+    C, S, nimg, ncand, world = 4, 7, 3, 20, 2
+    cfg = engine.Config(subpalette_count=C, subpalette_size=S)
+
+    def make():
+        ims = [engine.OptimizedImage(ctx, synth.image(300 + j, "V"), cfg) for j in range(nimg)]
+        engine.batch_initialize_tiles(ims)
+        engine.batch_recalculate_palettes(ims)
+        return ims
+    single, ranks = make(), [make() for _ in range(world)]
+    cand = np.stack([synth.candidates(300 + j, 0, ncand) for j in range(nimg)])
+    cand[:, 15] = cand[:, 2]                     # a tie across the two slices: the lower index must win
+    want, _ = engine.batch_step_random(single, 2, 3, cand)
+    dev = torch.device("cuda", 0)
+    local = [torch.zeros(nimg * 2, dtype=torch.int64, device=dev) for _ in range(world)]
+    for r in range(world):
+        lo, hi = driver.shard_bounds(ncand, r, world)
+        engine.batch_step_random_shard_begin(ranks[r], 2, 3, cand, lo, hi - lo, local[r].data_ptr())
+    ctx.synchronize()
+    gathered = torch.cat(local)
+    for r in range(world):
+        got, errs = engine.batch_step_random_shard_end(ranks[r], 2, 3, gathered.data_ptr(), world, nimg, want_errors=True)
+        assert np.array_equal(got["idx"], want["idx"]) and np.array_equal(got["err"], want["err"])
+        for a, b in zip(ranks[r], single):
+            assert a.state_checksum() == b.state_checksum()
+        assert np.array_equal(errs, engine.batch_error(single))
+    with pytest.raises(engine.SnesGpuError):     # a list with a colour component above 32 is refused at the boundary
+        bad = cand.copy()
+        bad[0, 0, 0] = 33
+        engine.batch_step_random_shard_begin(ranks[0], 2, 3, bad, 0, ncand, local[0].data_ptr())
+    for im in single + sum(ranks, []):
+        im.close()
+
+
+def test_device_candidate_lists_are_range_checked(ctx):
+    """the *_dev entry points take candidate bytes the host never sees.  A component above 32 must neither index
+    outside the BGR555 -> Lab table nor reach the image's palette; the next snes_ctx_synchronize() reports it."""
+    import torch
+    cfg = engine.Config(subpalette_count=2, subpalette_size=4, perceptual_palettes=True)
+    g = engine.OptimizedImage(ctx, synth.image(310, "V"), cfg)
+    g.initialize_tiles()
+    g.recalculate_palettes()
+    before = g.palette.copy()
+    dev = torch.device("cuda", 0)
+    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream or 1)
+    try:
+        cand = torch.tensor([[[200, 255, 77], [255, 255, 255]]], dtype=torch.uint8, device=dev)
+        best = torch.zeros(2, dtype=torch.int64, device=dev)
+        engine.batch_error_eval_candidates_dev([g], 1, 2, cand.data_ptr(), 2, 0, None, best.data_ptr())
+        engine.batch_apply_best_dev([g], 1, 2, cand.data_ptr(), 2, best.data_ptr())
+        with pytest.raises(engine.SnesGpuError):
+            ctx.synchronize()
+        ctx.synchronize()                        # the flag is reported once
+    finally:
+        ctx.set_stream(None)
+    assert np.array_equal(g.palette, before)
+    g.close()
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(dither=True), dict(perceptual_palettes=True)])
+def test_multi_entry_launch_matches_oracle_per_entry(ctx, kw):
+    """SURVEY 8(f) row 4 at kernel level: the candidates of EVERY palette entry evaluated against one state in one launch
+    sequence (snes_batch_eval_candidates_multi; the kernels read the replaced entry per evaluation) give, entry by entry, the
+    oracle's `colours[entry] = cand; optimize(); error()` scores and first minima -- and what one call per entry gives."""
+    C, S, ncand = 3, 4, 5
+    lab = bool(kw.get("perceptual_palettes"))
+    rgba = synth.image(77, "T")
+    g, o = make_pair(ctx, rgba, C, S, random_state=False, dither=bool(kw.get("dither")), lab=lab)
+    for im in (g, o):
+        im.initialize_tiles()
+        im.recalculate_palettes()
+    if lab:
+        o.palette = g.palette
+        o.optimize()
+    steps = [(p, i) for p in range(C) for i in range(S)]
+    cand = np.stack([synth.candidates(77, s, ncand) for s in range(len(steps))])
+    cand[5, 2] = o.palette[5]                      # one candidate equal to its entry's current colour
+    r = engine.batch_eval_candidates_multi([g], steps, cand[None])
+    tol = 1e-4 if lab else TIGHT_TOL
+    for s, (p, i) in enumerate(steps):
+        so = o.eval_candidates(p, i, cand[s])
+        assert np.max(np.abs(r["scores"][0, s] - so)) <= tol, (s, p, i)
+        single = engine.batch_eval_candidates([g], p, i, cand[s][None])
+        assert np.array_equal(single["scores"][0], r["scores"][0, s]), (s, p, i)      # bitwise what one call per entry gives
+        assert r["best"]["idx"][0, s] == int(np.argmin(r["scores"][0, s])) and r["best"]["err"][0, s] == r["scores"][0, s].min()
+    assert np.array_equal(g.palette, o.palette)     # the image's own state is untouched
+    g.close()
+
+
 def test_fused_error_and_candidates_matches_separate_calls(ctx):
     """snes_batch_error_eval_candidates_dev (error() items riding in the candidates' scorer launch) must give what
     snes_batch_error_dev followed by snes_batch_eval_candidates_dev gives, bit for bit, and leave the same cached errors."""

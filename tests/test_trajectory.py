@@ -67,6 +67,16 @@ def test_trajectory_rgb_metric_bit_exact(ctx, name):
     assert r.image.as_json() == o.as_json()
     assert (r.cursor.palette, r.cursor.palette_index, r.cursor.step) == (cur.palette, cur.palette_index, cur.step)
     assert accepted >= 3, "the trajectory should move: most early iterations find a better colour"
+    # the same iterations asked for in one go: the runner evaluates several entries ahead per call (snes_image_iterate) and
+    # must land on the same trajectory -- state, cursor and the log of error changes
+    r2 = driver.HeadlessRunner(ctx, rgba, cfg, seed=0, ncand=64, speculate=4)
+    r2.initialize()
+    r2.iterate(ITERATIONS)
+    assert np.array_equal(r2.image.palette, o.palette) and np.array_equal(r2.image.palette_map, o.palette_map), name
+    assert r2.image.as_json() == o.as_json()
+    assert (r2.cursor.palette, r2.cursor.palette_index, r2.cursor.step, r2.iteration) == (cur.palette, cur.palette_index, cur.step, ITERATIONS)
+    assert r2.log == r.log and abs(r2.image.error() - o.error()) <= TIGHT_TOL
+    r2.image.close()
     r.image.close()
 
 
