@@ -488,13 +488,23 @@ def measure_configs(ctx, iters: int = 100) -> dict:
         r.iterate(3)
         ctx.synchronize()
         t2 = time.perf_counter()
+        moves0 = len(r.log)
         r.iterate(iters)
         ctx.synchronize()
         t3 = time.perf_counter()
+        moves1, e1 = len(r.log), r.image.error()
+        later = 4 * iters
+        r.iterate(later)                     # further down the same trajectory fewer iterations find a better colour
+        ctx.synchronize()
+        t4 = time.perf_counter()
         per_iter = 56 if cfg.nes else 64
         out[name] = {"init_ms": 1e3 * (t1 - t0), "ms_per_iteration": 1e3 * (t3 - t2) / iters, "iterations": iters,
                      "candidate_evals_per_s": iters * per_iter / (t3 - t2), "candidates_per_iteration": per_iter,
-                     "error_start": e0, "error_end": r.image.error(), "config": kw}
+                     "iterations_that_moved": moves1 - moves0, "error_start": e0, "error_end": e1,
+                     "next_iterations": later, "next_ms_per_iteration": 1e3 * (t4 - t3) / later,
+                     "next_candidate_evals_per_s": later * per_iter / (t4 - t3), "next_iterations_that_moved": len(r.log) - moves1,
+                     "error_after_all": r.image.error(), "lookahead_iterations_per_call": "adaptive (driver.HeadlessRunner.lookahead)",
+                     "config": kw}
         r.image.close()
     return out
 

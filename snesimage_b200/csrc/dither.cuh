@@ -24,7 +24,7 @@ namespace snes {
 
 constexpr int DITHER_THREADS = 128;
 #ifndef DITHER_SHFL
-#define DITHER_SHFL 1
+#define DITHER_SHFL 0   // A/B on B200 (profiles/r2_dither_ab.txt): shuffles + ring 6.12 ms per 4096 evaluations at 8x15, mailbox + barrier 4.61
 #endif
 constexpr int DITHER_RING = 16;      // steps a producing warp may run ahead of the warp that consumes its last row
 #ifndef DITHER_MIN_CTAS

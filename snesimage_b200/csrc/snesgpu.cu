@@ -598,6 +598,9 @@ struct EvalPlan {
     uint8_t *d_maps_out = nullptr;    // optional [E][NPIX] device: keep every palette_map
     double *d_scores = nullptr;       // [E] device output of do_score
     const TileMove *d_moves = nullptr;  // [E] device: tile-reassignment candidates (ovr < 0); null = none
+    bool no_pool = false;             // leave the partial sums unpooled (the caller's finishing kernel pools them)
+    bool self_fresh = false;          // every image's palette_map is optimize() of its current state: its coarse pyramid is the
+                                      // prepared base assignment's, so error() of the images needs no pyramid of its own
     bool with_self_error = false;     // also error() of every image's own state -> ctx->self_scores and the image's cached
                                       // error, scored inside the first chunk's launch (k_score_v3 only; lib.rs:199, 294)
 };
@@ -644,9 +647,13 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
     const bool delta_path = ctx->delta && !cfg.dither && pl.do_assign && pl.do_score && !pl.self && !pl.d_maps_out &&
                             pl.ovr >= 0 && CS <= 255;
     FusedArgs fself;
+    const int pyr_gx = pl.nimg < 16 ? 64 : 16;   // few images: one 32x32 region per CTA instead of four in a row
+    float *base_xyb = ctx->self_xyb + (size_t)ctx->img_cap * EVAL_XYB_FLOATS;
+    const bool share_base = self_too && delta_path && pl.self_fresh;
     if (self_too) {  // the coarse pyramid of the images' own palette_map: input of their error()
-        LAUNCH(ctx, "k_pyramid<false>", k_pyramid<false><<<dim3(16, pl.nimg), 256, 0, st>>>(ctx->d_imgs, ctx->cents, 1, 0, S, CS, -1, nullptr, 1,
-                                                       ctx->self_xyb, 0));
+        if (!share_base)
+            LAUNCH(ctx, "k_pyramid<false>", k_pyramid<false><<<dim3(pyr_gx, pl.nimg), 256, 0, st>>>(ctx->d_imgs, ctx->cents, 1, 0, S, CS, -1, nullptr, 1,
+                                                           ctx->self_xyb, 0));
         fself.imgs = ctx->d_imgs;
         fself.cents = ctx->cents;
         fself.ncand = 1;
@@ -657,7 +664,7 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
         fself.maps = nullptr;
         fself.from_image = 1;
         fself.gi_fmt = 0;
-        fself.xyb_rm = ctx->self_xyb;
+        fself.xyb_rm = share_base ? base_xyb : ctx->self_xyb;
         fself.partials = ctx->self_partials;
     }
 
@@ -670,8 +677,8 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
             LAUNCH(ctx, "k_assign_prepare<false>", k_assign_prepare<false><<<dim3(64, pl.nimg), 256, 0, st>>>(ctx->d_imgs, S, CS));
         // coarse pyramid of the prepared base assignment (current palette, no candidate): k_assign_pyr copies the blocks
         // a candidate leaves unchanged from it
-        LAUNCH(ctx, "k_pyramid<false>", k_pyramid<false><<<dim3(16, pl.nimg), 256, 0, st>>>(ctx->d_imgs, ctx->cents, 1, 0, S, CS, -1, nullptr, 2,
-                                                       ctx->self_xyb + (size_t)ctx->img_cap * EVAL_XYB_FLOATS, 1));
+        LAUNCH(ctx, "k_pyramid<false>", k_pyramid<false><<<dim3(pyr_gx, pl.nimg), 256, 0, st>>>(ctx->d_imgs, ctx->cents, 1, 0, S, CS, -1, nullptr, 2,
+                                                       base_xyb, 1));
     }
 
     for (int e0 = 0; e0 < E; e0 += chunk) {
@@ -749,12 +756,20 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
         fa.partials = ctx->partials;
         RET(launch_scorer(ctx, fa, ec, (self_too && e0 == 0) ? &fself : nullptr, pl.nimg));
     }
+    if (pl.no_pool) return SNES_OK;
     if (self_too) {
-        LAUNCH(ctx, "k_pool_fused", k_pool_fused<<<(pl.nimg + 127) / 128, 128, 0, st>>>(ctx->self_partials, pl.nimg, ctx->self_scores));
+        LAUNCH(ctx, "k_pool_fused", k_pool_fused<<<(pl.nimg + 3) / 4, 128, 0, st>>>(ctx->self_partials, pl.nimg, ctx->self_scores));
         LAUNCH(ctx, "k_store_cur_err", k_store_cur_err<<<(pl.nimg + 127) / 128, 128, 0, st>>>(ctx->d_imgs, pl.nimg, ctx->self_scores));
     }
-    if (pl.do_score) LAUNCH(ctx, "k_pool_fused", k_pool_fused<<<(E + 127) / 128, 128, 0, st>>>(ctx->partials, E, pl.d_scores));
+    if (pl.do_score) LAUNCH(ctx, "k_pool_fused", k_pool_fused<<<(E + 3) / 4, 128, 0, st>>>(ctx->partials, E, pl.d_scores));
     return SNES_OK;
+}
+
+// every image's palette_map is optimize() of its current palette and tile assignment
+static bool all_fresh(snes_image *const *images, int nimg) {
+    for (int j = 0; j < nimg; j++)
+        if (!images[j]->map_fresh) return false;
+    return true;
 }
 
 // optimize() of every image in the batch (lib.rs:425-501)
@@ -1183,6 +1198,7 @@ static int eval_candidates_dev(snes_ctx *ctx, snes_image *const *images, int nim
     pl.do_assign = pl.do_score = true;
     pl.d_scores = d_scores ? d_scores : ctx->scores;
     pl.with_self_error = with_error && ctx->fused == 3;
+    pl.self_fresh = all_fresh(images, nimg);
     RET(run_plan(ctx, cfg, pl));
     if (d_best) {
         LAUNCH(ctx, "k_argmin", k_argmin<<<nimg, 128, 0, ctx->stream>>>(pl.d_scores, ncand, cand_idx_base, reinterpret_cast<Best *>(d_best)));
@@ -1387,6 +1403,7 @@ static int batch_step(snes_ctx *ctx, snes_image *const *images, int nimg, int pa
     pl.do_assign = pl.do_score = true;
     pl.d_scores = ctx->scores;
     pl.with_self_error = mode != 1 && ctx->fused == 3;
+    pl.self_fresh = all_fresh(images, nimg);
     RET(run_plan(ctx, cfg, pl));
     LAUNCH(ctx, "k_argmin", k_argmin<<<nimg, 128, 0, st>>>(ctx->scores, ncand, 0, ctx->best));
     LAUNCH(ctx, "k_apply_best", k_apply_best<<<(nimg + 127) / 128, 128, 0, st>>>(ctx->d_imgs, nimg, slot, ctx->cand, ncand, ctx->best, mode == 1));
@@ -1484,7 +1501,7 @@ struct MultiLayout {   // offsets into ctx->d_ints
 // mode 0: explicit candidates cand[nimg][nsteps][ncand][3] (host); 1: the 56 NES colours; 2: the 32 values of steps[s].channel.
 // Leaves scores in ctx->scores ([nimg][nsteps][ncand]) and the per-step first minima in ctx->best_m ([nimg][nsteps]).
 static int eval_multi(snes_ctx *ctx, snes_image *const *images, int nimg, int mode, const snes_step *steps, int nsteps, const uint8_t *cand,
-                      int &ncand, bool with_error, MultiLayout &lay) {
+                      int &ncand, bool with_error, MultiLayout &lay, bool finish_later = false) {
     RET(bind_images(ctx, images, nimg));
     const snes_config cfg = images[0]->cfg;
     if (!steps || nsteps < 1 || nsteps > 4096) return fail(SNES_E_INVALID, "multi-entry call: need 1..4096 steps");
@@ -1503,7 +1520,7 @@ static int eval_multi(snes_ctx *ctx, snes_image *const *images, int nimg, int mo
             if (cand[i] > 32) return fail(SNES_E_INVALID, "colour component > 32");
     RET(ensure_evals(ctx, E));
     RET(ensure_ints(ctx, (size_t)per_img + 2 * nsteps + 2 * nimg));
-    RET(ensure_best_m(ctx, (size_t)nimg * nsteps));
+    RET(ensure_best_m(ctx, (size_t)nimg * nsteps + nimg));   // + nimg records' worth of doubles: errors before / after (iterate)
     lay.slots = ctx->d_ints;
     lay.step_slot = lay.slots + per_img;
     lay.step_channel = lay.step_slot + nsteps;
@@ -1531,8 +1548,10 @@ static int eval_multi(snes_ctx *ctx, snes_image *const *images, int nimg, int mo
     pl.do_assign = pl.do_score = true;
     pl.d_scores = ctx->scores;
     pl.with_self_error = with_error && ctx->fused == 3;
+    pl.no_pool = finish_later;
+    pl.self_fresh = all_fresh(images, nimg);
     RET(run_plan(ctx, cfg, pl));
-    LAUNCH(ctx, "k_argmin", k_argmin<<<nimg * nsteps, 128, 0, st>>>(ctx->scores, ncand, 0, ctx->best_m));
+    if (!finish_later) LAUNCH(ctx, "k_argmin", k_argmin<<<nimg * nsteps, 128, 0, st>>>(ctx->scores, ncand, 0, ctx->best_m));
     return SNES_OK;
 }
 
@@ -1557,14 +1576,26 @@ static int iterate_multi(snes_ctx *ctx, snes_image *const *images, int nimg, int
                          int ncand, int *consumed, double *errors_before, double *errors_after) {
     MultiLayout lay;
     if (mode == 1 && nsteps != 1) return fail(SNES_E_INVALID, "NES iterations always replace the entry (lib.rs:250): one step per call");
-    RET(eval_multi(ctx, images, nimg, mode, steps, nsteps, cand, ncand, mode != 1, lay));
+    // one finishing kernel (error() of the images, first minima, first accept) after the candidates' pooling when the scorer
+    // hands over the images' own partial sums; else the separate kernels
+    const bool fuse_finish = ctx->fused == 3;
+    RET(eval_multi(ctx, images, nimg, mode, steps, nsteps, cand, ncand, mode != 1, lay, fuse_finish));
     const snes_config cfg = images[0]->cfg;
     cudaStream_t st = ctx->stream;
     const int per_img = nsteps * ncand;
-    // error() of the state the steps were evaluated against (lib.rs:199, 294); NES steps do not compute it (lib.rs:250)
-    if (errors_before && mode != 1) CK(cudaMemcpyAsync(errors_before, ctx->self_scores, sizeof(double) * nimg, cudaMemcpyDeviceToHost, st));
-    LAUNCH(ctx, "k_apply_first_accept", k_apply_first_accept<<<(nimg + 127) / 128, 128, 0, st>>>(ctx->d_imgs, nimg, lay.step_slot, nsteps, ctx->cand, ncand,
-                                                                           ctx->best_m, mode == 1, lay.consumed, lay.chosen));
+    double *d_before = reinterpret_cast<double *>(ctx->best_m + (size_t)nimg * nsteps), *d_after = d_before + nimg;
+    if (fuse_finish) {
+        LAUNCH(ctx, "k_pool_fused", k_pool_fused<<<(nimg * per_img + 3) / 4, 128, 0, st>>>(ctx->partials, nimg * per_img, ctx->scores));
+        LAUNCH(ctx, "k_finish_iterate", k_finish_iterate<<<nimg, 128, 0, st>>>(ctx->d_imgs, mode != 1 ? ctx->self_partials : nullptr, ctx->scores,
+                                                                           lay.step_slot, nsteps, ctx->cand, ncand, mode == 1, ctx->best_m,
+                                                                           lay.consumed, lay.chosen, d_before, d_after));
+        if (errors_before && mode != 1) CK(cudaMemcpyAsync(errors_before, d_before, sizeof(double) * nimg, cudaMemcpyDeviceToHost, st));
+    } else {
+        // error() of the state the steps were evaluated against (lib.rs:199, 294); NES steps do not compute it (lib.rs:250)
+        if (errors_before && mode != 1) CK(cudaMemcpyAsync(errors_before, ctx->self_scores, sizeof(double) * nimg, cudaMemcpyDeviceToHost, st));
+        LAUNCH(ctx, "k_apply_first_accept", k_apply_first_accept<<<(nimg + 127) / 128, 128, 0, st>>>(ctx->d_imgs, nimg, lay.step_slot, nsteps, ctx->cand, ncand,
+                                                                               ctx->best_m, mode == 1, lay.consumed, lay.chosen));
+    }
     bool fresh = cfg.subpalette_count * cfg.subpalette_size <= 255 && (size_t)nimg * per_img <= (size_t)ctx->chunk;
     for (int j = 0; j < nimg; j++) fresh = fresh && images[j]->map_fresh;
     if (fresh) {
@@ -1573,7 +1604,9 @@ static int iterate_multi(snes_ctx *ctx, snes_image *const *images, int nimg, int
         RET(batch_optimize(ctx, images, nimg));   // stale palette_map, or the scratch maps of the first chunks are gone
     }
     if (consumed) CK(cudaMemcpyAsync(consumed, lay.consumed, sizeof(int) * nimg, cudaMemcpyDeviceToHost, st));
-    if (errors_after) {
+    if (errors_after && fuse_finish) {
+        CK(cudaMemcpyAsync(errors_after, d_after, sizeof(double) * nimg, cudaMemcpyDeviceToHost, st));
+    } else if (errors_after) {
         LAUNCH(ctx, "k_load_cur_err", k_load_cur_err<<<(nimg + 127) / 128, 128, 0, st>>>(ctx->d_imgs, nimg, ctx->self_scores));
         CK(cudaMemcpyAsync(errors_after, ctx->self_scores, sizeof(double) * nimg, cudaMemcpyDeviceToHost, st));
     }
