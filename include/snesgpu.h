@@ -206,11 +206,11 @@ int snes_batch_eval_candidates_multi(snes_ctx *ctx, snes_image *const *images, i
  * in one call, exactly the reference's trajectory: all steps' candidates are evaluated against the current state, then the
  * steps are taken in order up to and including the first one that accepts a candidate (an iteration that accepts nothing
  * leaves the state it was evaluated against, so evaluating the next one early changes nothing).  mode 0: random, cand =
- * nsteps*ncand*3 explicit colours (the reference's rand::rng() draws, lib.rs:205-208); 1: NES (one step per call: it always
- * replaces the entry, lib.rs:250); 2: channel (32 values of steps[s].channel).  *consumed = iterations the call stands for
+ * nsteps*ncand*3 explicit colours (the reference's rand::rng() draws, lib.rs:205-208); 1: NES (a step always takes its first
+ * minimum, lib.rs:250, and ends the run only when that changes the entry's colour); 2: channel (32 values of steps[s].channel).  *consumed = iterations the call stands for
  * (the caller advances its cursor by that many and drops the rest of the list), *error_before = error() of the state the
- * call started from (what every iteration before the accepting one ends with; not computed in NES mode), *error_after =
- * error() of the new state. */
+ * call started from (what every iteration before the accepting one ends with; in NES mode NaN unless such an iteration
+ * exists), *error_after = error() of the new state. */
 int snes_image_iterate(snes_image *im, int mode, const snes_step *steps, int nsteps, const uint8_t *cand, int ncand,
                        int *consumed, double *error_before, double *error_after);
 

@@ -506,10 +506,11 @@ __global__ void k_apply_tile_move(const ImgDev *imgs, int nimg, const TileMove *
 // reference runs them one after the other, lib.rs:889-933, and an iteration that finds nothing better leaves the state
 // as it was, so the next iteration's evaluations against the old state are exactly the reference's).  best[j][s] is the
 // first minimum of step s's candidates.  Steps are taken in order; the first whose best beats the image's current error
-// (lib.rs:216-219; force: NES, lib.rs:250) is applied and ends the run: consumed[j] = its number + 1 (nsteps if none),
+// (lib.rs:216-219) is applied and ends the run; a NES step (force, lib.rs:250) always takes its first minimum and ends the
+// run only if that changes the entry's colour: consumed[j] = the last step's number + 1 (nsteps if none),
 // chosen[j] = the accepted evaluation's index among the image's nsteps * ncand evaluations, or -1.
 __global__ void k_apply_first_accept(const ImgDev *imgs, int nimg, const int *step_slot, int nsteps, const uint8_t *cand, int ncand,
-                                     const Best *best, int force, int *consumed, int *chosen) {
+                                     const Best *best, int force, int *consumed, int *chosen, double *err_before /* NES only, or null */) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nimg) return;
     const ImgDev im = imgs[j];
@@ -519,8 +520,14 @@ __global__ void k_apply_first_accept(const ImgDev *imgs, int nimg, const int *st
         if (b.idx < 0 || b.idx >= ncand) continue;
         const uint8_t *c = cand + (((size_t)j * nsteps + s) * ncand + b.idx) * 3;
         if (c[0] > 32 || c[1] > 32 || c[2] > 32) continue;
+        const int slot = step_slot[s];
+        const uint8_t *cur = im.palette + 3 * slot;
+        if (force && c[0] == cur[0] && c[1] == cur[1] && c[2] == cur[2]) {   // NES step that leaves the colour as it is
+            *im.cur_err = b.err;
+            if (err_before) err_before[j] = b.err;
+            continue;
+        }
         if (force || b.err < *im.cur_err) {
-            const int slot = step_slot[s];
             im.palette[3 * slot] = c[0];
             im.palette[3 * slot + 1] = c[1];
             im.palette[3 * slot + 2] = c[2];

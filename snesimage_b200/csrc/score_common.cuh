@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(128) k_pool_fused(const double *partials, int 
 // k_finish_iterate: what follows the pooling of the candidates' scores (k_pool_fused) in the speculative single-call
 // iterations (snes_image_iterate), one CTA per image instead of four more launches: error() of the image itself (-> its
 // current error), the strict-< first minimum of every step's list (lib.rs:216), then the steps in order up to the first
-// one whose best beats the current error (k_apply_first_accept's rule).  grid = nimg, block 128.
+// one whose best beats the current error (k_apply_first_accept's rule; a NES step always takes its first minimum, and ends
+// the run only if that changes the entry's colour).  grid = nimg, block 128.
 __global__ void __launch_bounds__(128) k_finish_iterate(const ImgDev *imgs, const double *self_partials /* null: NES, no error() first */,
                                                        const double *scores, const int *step_slot, int nsteps,
                                                        const uint8_t *cand, int ncand, int force, Best *best, int *consumed, int *chosen,
@@ -132,8 +133,14 @@ __global__ void __launch_bounds__(128) k_finish_iterate(const ImgDev *imgs, cons
             best[(size_t)j * nsteps + s] = b;
             if (pick < 0 && used == nsteps && b.idx >= 0) {
                 const uint8_t *c = cand + (((size_t)j * nsteps + s) * ncand + b.idx) * 3;
-                if (c[0] <= 32 && c[1] <= 32 && c[2] <= 32 && (force || b.err < *im.cur_err)) {
-                    const int slot = step_slot[s];
+                const int slot = step_slot[s];
+                const uint8_t *cur = im.palette + 3 * slot;
+                if (force && c[0] == cur[0] && c[1] == cur[1] && c[2] == cur[2]) {
+                    // NES iteration (lib.rs:242-284) whose first minimum is the colour the entry already has: the state stays what
+                    // the later steps were evaluated against, and its error() is this evaluation's score
+                    *im.cur_err = b.err;
+                    err_before[j] = b.err;
+                } else if (c[0] <= 32 && c[1] <= 32 && c[2] <= 32 && (force || b.err < *im.cur_err)) {
                     im.palette[3 * slot] = c[0];
                     im.palette[3 * slot + 1] = c[1];
                     im.palette[3 * slot + 2] = c[2];

@@ -1575,7 +1575,6 @@ extern "C" int snes_batch_eval_candidates_multi(snes_ctx *ctx, snes_image *const
 static int iterate_multi(snes_ctx *ctx, snes_image *const *images, int nimg, int mode, const snes_step *steps, int nsteps, const uint8_t *cand,
                          int ncand, int *consumed, double *errors_before, double *errors_after) {
     MultiLayout lay;
-    if (mode == 1 && nsteps != 1) return fail(SNES_E_INVALID, "NES iterations always replace the entry (lib.rs:250): one step per call");
     // one finishing kernel (error() of the images, first minima, first accept) after the candidates' pooling when the scorer
     // hands over the images' own partial sums; else the separate kernels
     const bool fuse_finish = ctx->fused == 3;
@@ -1584,17 +1583,20 @@ static int iterate_multi(snes_ctx *ctx, snes_image *const *images, int nimg, int
     cudaStream_t st = ctx->stream;
     const int per_img = nsteps * ncand;
     double *d_before = reinterpret_cast<double *>(ctx->best_m + (size_t)nimg * nsteps), *d_after = d_before + nimg;
+    if (mode == 1) CK(cudaMemsetAsync(d_before, 0xff, sizeof(double) * nimg, st));   // NaN unless a NES step left its entry as it was
     if (fuse_finish) {
         LAUNCH(ctx, "k_pool_fused", k_pool_fused<<<(nimg * per_img + 3) / 4, 128, 0, st>>>(ctx->partials, nimg * per_img, ctx->scores));
         LAUNCH(ctx, "k_finish_iterate", k_finish_iterate<<<nimg, 128, 0, st>>>(ctx->d_imgs, mode != 1 ? ctx->self_partials : nullptr, ctx->scores,
                                                                            lay.step_slot, nsteps, ctx->cand, ncand, mode == 1, ctx->best_m,
                                                                            lay.consumed, lay.chosen, d_before, d_after));
-        if (errors_before && mode != 1) CK(cudaMemcpyAsync(errors_before, d_before, sizeof(double) * nimg, cudaMemcpyDeviceToHost, st));
+        if (errors_before) CK(cudaMemcpyAsync(errors_before, d_before, sizeof(double) * nimg, cudaMemcpyDeviceToHost, st));
     } else {
         // error() of the state the steps were evaluated against (lib.rs:199, 294); NES steps do not compute it (lib.rs:250)
         if (errors_before && mode != 1) CK(cudaMemcpyAsync(errors_before, ctx->self_scores, sizeof(double) * nimg, cudaMemcpyDeviceToHost, st));
         LAUNCH(ctx, "k_apply_first_accept", k_apply_first_accept<<<(nimg + 127) / 128, 128, 0, st>>>(ctx->d_imgs, nimg, lay.step_slot, nsteps, ctx->cand, ncand,
-                                                                               ctx->best_m, mode == 1, lay.consumed, lay.chosen));
+                                                                               ctx->best_m, mode == 1, lay.consumed, lay.chosen,
+                                                                               mode == 1 ? d_before : nullptr));
+        if (errors_before && mode == 1) CK(cudaMemcpyAsync(errors_before, d_before, sizeof(double) * nimg, cudaMemcpyDeviceToHost, st));
     }
     bool fresh = cfg.subpalette_count * cfg.subpalette_size <= 255 && (size_t)nimg * per_img <= (size_t)ctx->chunk;
     for (int j = 0; j < nimg; j++) fresh = fresh && images[j]->map_fresh;

@@ -347,9 +347,8 @@ class HeadlessRunner:
         done = 0
         while done < n:
             mode = c.mode(self.config)
-            # the iterations ahead of the cursor that share this one's mode (NES iterations always replace their entry,
-            # lib.rs:250, so nothing can be evaluated ahead of them)
-            ahead = 1 if mode == "nes" else min(self.lookahead(), n - done)
+            # the iterations ahead of the cursor that share this one's mode
+            ahead = min(self.lookahead(), n - done)
             steps, cands, look = [], [], Cursor(c.palette, c.palette_index, c.channel, c.step)
             for k in range(ahead):
                 if look.mode(self.config) != mode:
@@ -360,11 +359,11 @@ class HeadlessRunner:
                 look.advance(self.config)
             # optimize_palette_entry_* + optimize() + error() (lib.rs:892-910) of `used` iterations in one call
             used, before, error = im.iterate(mode, steps, np.stack(cands) if cands else None)
-            if mode != "nes":
-                accepted = 1.0 if (used < len(steps) or error != before) else 0.0
-                self.accept_rate += 0.25 * (accepted / used - self.accept_rate)
+            # did the run end on an iteration that changed the palette?  (a NES run that used every step may have: counted as not)
+            accepted = 1.0 if (used < len(steps) or (mode != "nes" and error != before)) else 0.0
+            self.accept_rate += 0.25 * (accepted / used - self.accept_rate)
             # lib.rs:912-915 per iteration: the iterations before the last consumed one ended with the error they started from
-            for e in ([before] if used > 1 else []) + [error]:
+            for e in ([before] if used > 1 and before == before else []) + [error]:
                 if abs(e - self.last_error) > np.finfo(np.float64).eps:
                     self.last_error = e
                     self.log.append(e)
