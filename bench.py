@@ -317,11 +317,11 @@ def run_ours(args):
         job.step_dev(it)
     clocks = ClockSampler(local)
     launches0 = ctx.kernel_launches
-    ctx.profile_begin()
+    ctx.profile_begin(only="k_score")          # event pairs around the dominant kernel only: the timed region stays undisturbed
     clocks.start()
     ms = timed(job.step_dev, range(args.warmup, nsteps))
     clock_info = clocks.stop()
-    prof = ctx.profile_end()
+    prof_top = ctx.profile_end()
     launches = ctx.kernel_launches - launches0
     evals_per_step = job.evals_per_step
     value = evals_per_step * args.steps / (ms * 1e-3)
@@ -331,6 +331,13 @@ def run_ours(args):
         job.step_host(it)
     ms_e2e = timed(job.step_host, range(args.warmup, nsteps))
     e2e_value = evals_per_step * args.steps / (ms_e2e * 1e-3)
+    # every kernel's CUDA-event time per step, from an extra (untimed) pass over the same steps
+    ctx.profile_begin()
+    for it in range(args.warmup, nsteps):
+        job.step_dev(it)
+    prof = ctx.profile_end()
+    for k, v in prof_top.items():
+        prof[k] = v                            # the dominant kernel's figures are the timed region's own
     sums = gather_checksums(job)
     h2d = int(job.cand_host[0].nbytes)
     d2h = int(job.plan.nloc * 16)

@@ -81,6 +81,9 @@ int snes_ctx_synchronize(snes_ctx *ctx);
  * disables, synchronises and writes a JSON object {"<kernel>": {"ms": total, "n": launches}, ...}
  * (at most cap-1 bytes + NUL; *len = full length). */
 int snes_ctx_profile_begin(snes_ctx *ctx);
+/* restrict the event pairs to launches whose kernel name contains name_part (NULL or "": every launch).  Two event records
+ * per launch are cheap but not free: a timed region of many short steps brackets its dominant kernel only. */
+int snes_ctx_profile_only(snes_ctx *ctx, const char *name_part);
 int snes_ctx_profile_end(snes_ctx *ctx, char *buf, size_t cap, size_t *len);
 /* kernel selection (both scorers give the same f32 planes; kept switchable for A/B checks):
  *   fused             3 = k_score_v3 (default: persistent 4-warp CTAs, TMA staging, packed-f32 horizontal pass),

@@ -466,10 +466,12 @@ __global__ void k_merge_best(const Best *gathered, int nranks, int rank_stride /
 // than the current error) or lib.rs:250/264/280 (NES: always the first minimum).  One thread per
 // image; rewrites the palette entry and the image's cached error.
 // ------------------------------------------------------------------------------------------------
+// chosen[j] (optional) = index of the accepted candidate in the full list, or -1: what k_adopt_map copies the palette_map of.
 __global__ void k_apply_best(const ImgDev *imgs, int nimg, int slot, const uint8_t *cand_all, int ncand_all,
-                             const Best *best, int force) {
+                             const Best *best, int force, int *chosen = nullptr) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nimg) return;
+    if (chosen) chosen[j] = -1;
     const Best b = best[j];
     if (b.idx < 0 || b.idx >= ncand_all) return;
     const ImgDev im = imgs[j];
@@ -480,6 +482,7 @@ __global__ void k_apply_best(const ImgDev *imgs, int nimg, int slot, const uint8
         im.palette[3 * slot + 1] = c[1];
         im.palette[3 * slot + 2] = c[2];
         *im.cur_err = b.err;
+        if (chosen) chosen[j] = b.idx;
     }
 }
 

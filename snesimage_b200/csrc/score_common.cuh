@@ -72,6 +72,59 @@ __global__ void __launch_bounds__(128) k_pool_fused(const double *partials, int 
     if (lane == 0) scores[e] = v;
 }
 
+// k_pool_argmin: the end of a candidate step in one launch instead of four: error() of image j itself from its own partial
+// sums (-> its current error and self_scores[j]; skipped when self_partials is null), error() of its ncand candidate
+// evaluations, and their strict-< first minimum (lib.rs:216) as (error, idx_base + k).  grid = nimg, block 1024: 32 warps,
+// one evaluation per warp at a time.
+__global__ void __launch_bounds__(1024) k_pool_argmin(const ImgDev *imgs, const double *self_partials, double *self_scores,
+                                                     const double *partials, int ncand, int idx_base, double *scores, Best *best) {
+    __shared__ double s_e[32];
+    __shared__ int s_i[32];
+    const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double be = __longlong_as_double(0x7ff0000000000000ll);
+    int bi = 0x7fffffff;
+    for (int k = warp; k < ncand; k += 32) {   // ascending k per warp: a strict < keeps the first minimum
+        const double v = pool_score_warp(partials + ((size_t)j * ncand + k) * PART_DOUBLES, lane);
+        if (lane == 0) scores[(size_t)j * ncand + k] = v;
+        if (v < be) {
+            be = v;
+            bi = k;
+        }
+    }
+    if (self_partials && warp == 31) {   // the warp with the fewest candidates
+        const double v = pool_score_warp(self_partials + (size_t)j * PART_DOUBLES, lane);
+        if (lane == 0) {
+            *imgs[j].cur_err = v;
+            self_scores[j] = v;
+        }
+    }
+    if (lane == 0) {
+        s_e[warp] = be;
+        s_i[warp] = bi;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        be = s_e[lane];
+        bi = s_i[lane];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const double oe = __shfl_xor_sync(0xffffffffu, be, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (best_less(oe, oi, be, bi)) {
+                be = oe;
+                bi = oi;
+            }
+        }
+        if (lane == 0) {
+            Best b;
+            b.err = be;
+            b.idx = bi == 0x7fffffff ? -1 : bi + idx_base;
+            b.pad = 0;
+            best[j] = b;
+        }
+    }
+}
+
 // k_finish_iterate: what follows the pooling of the candidates' scores (k_pool_fused) in the speculative single-call
 // iterations (snes_image_iterate), one CTA per image instead of four more launches: error() of the image itself (-> its
 // current error), the strict-< first minimum of every step's list (lib.rs:216), then the steps in order up to the first

@@ -87,12 +87,17 @@ struct snes_ctx {
     size_t ints_cap = 0;
     Best *best_m = nullptr;    // [nimg * nsteps] first minima of a multi-entry call
     size_t best_m_cap = 0;
+    bool maps_live = false;    // the scratch maps hold the gi maps of every evaluation of the last candidate step (one entry,
+    int maps_nimg = 0, maps_ncand = 0, maps_slot = -1;   // full candidate lists): [maps_nimg][maps_ncand][NPIX]
+    const uint8_t *maps_cand = nullptr;
+    std::vector<snes_image *> maps_images;
     int shard_ncand_all = 0;   // candidates per image of the list snes_batch_step_random_shard_begin left in `cand`
 
     float4 *labtab = nullptr;  // BGR555 -> Lab<D65,f32>
 
     // per-launch CUDA-event timing (snes_ctx_profile_begin/end)
-    bool profiling = false;
+    bool profiling = false, prof_skip = false;
+    std::string prof_filter;   // non-empty: only launches whose name contains it are bracketed by events
     std::vector<cudaEvent_t> prof_events;
     std::vector<const char *> prof_names;
     size_t prof_used = 0;
@@ -174,6 +179,8 @@ static int tm_make_evals(EvalTm *tm, const uint8_t *maps, const float *xyb, int 
 
 static void prof_begin(snes_ctx *ctx, const char *name) {
     if (!ctx->profiling) return;
+    ctx->prof_skip = !ctx->prof_filter.empty() && !strstr(name, ctx->prof_filter.c_str());
+    if (ctx->prof_skip) return;
     if (ctx->prof_used + 2 > ctx->prof_events.size()) {
         cudaEvent_t a, b;
         cudaEventCreate(&a);
@@ -185,7 +192,7 @@ static void prof_begin(snes_ctx *ctx, const char *name) {
     cudaEventRecord(ctx->prof_events[ctx->prof_used], ctx->stream);
 }
 static void prof_end(snes_ctx *ctx) {
-    if (!ctx->profiling) return;
+    if (!ctx->profiling || ctx->prof_skip) return;
     cudaEventRecord(ctx->prof_events[ctx->prof_used + 1], ctx->stream);
     ctx->prof_used += 2;
 }
@@ -430,6 +437,12 @@ extern "C" int snes_ctx_synchronize(snes_ctx *ctx) {
     return SNES_OK;
 }
 
+extern "C" int snes_ctx_profile_only(snes_ctx *ctx, const char *name_part) {
+    if (!ctx) return fail(SNES_E_INVALID, "ctx is NULL");
+    ctx->prof_filter = name_part ? name_part : "";
+    return SNES_OK;
+}
+
 extern "C" int snes_ctx_profile_begin(snes_ctx *ctx) {
     if (!ctx) return fail(SNES_E_INVALID, "ctx is NULL");
     ctx->profiling = true;
@@ -598,6 +611,8 @@ struct EvalPlan {
     uint8_t *d_maps_out = nullptr;    // optional [E][NPIX] device: keep every palette_map
     double *d_scores = nullptr;       // [E] device output of do_score
     const TileMove *d_moves = nullptr;  // [E] device: tile-reassignment candidates (ovr < 0); null = none
+    Best *d_best = nullptr;           // with do_score: also the strict-< first minimum of every image's evaluations, as
+    int best_idx_base = 0;            // (error, best_idx_base + k), pooled and reduced in one launch (k_pool_argmin)
     bool no_pool = false;             // leave the partial sums unpooled (the caller's finishing kernel pools them)
     bool self_fresh = false;          // every image's palette_map is optimize() of its current state: its coarse pyramid is the
                                       // prepared base assignment's, so error() of the images needs no pyramid of its own
@@ -756,7 +771,20 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
         fa.partials = ctx->partials;
         RET(launch_scorer(ctx, fa, ec, (self_too && e0 == 0) ? &fself : nullptr, pl.nimg));
     }
+    // what the last evaluation left in the scratch maps: snes_batch_apply_best_dev / batch_step adopt the accepted candidate's
+    // palette_map from there instead of running optimize() again
+    ctx->maps_live = pl.do_assign && pl.do_score && !pl.self && !pl.d_maps_out && !pl.d_moves && pl.ovr >= 0 && !pl.d_slots && CS <= 255 &&
+                     E <= chunk && pl.cand_lo == 0 && (pl.cand_stride == 0 || pl.cand_stride == pl.ncand);
+    ctx->maps_nimg = pl.nimg;
+    ctx->maps_ncand = pl.ncand;
+    ctx->maps_slot = pl.ovr;
+    ctx->maps_cand = pl.d_cand;
     if (pl.no_pool) return SNES_OK;
+    if (pl.do_score && pl.d_best && !pl.self) {
+        LAUNCH(ctx, "k_pool_argmin", k_pool_argmin<<<pl.nimg, 1024, 0, st>>>(ctx->d_imgs, self_too ? ctx->self_partials : nullptr, ctx->self_scores, ctx->partials,
+                                                                  pl.ncand, pl.best_idx_base, pl.d_scores, pl.d_best));
+        return SNES_OK;
+    }
     if (self_too) {
         LAUNCH(ctx, "k_pool_fused", k_pool_fused<<<(pl.nimg + 3) / 4, 128, 0, st>>>(ctx->self_partials, pl.nimg, ctx->self_scores));
         LAUNCH(ctx, "k_store_cur_err", k_store_cur_err<<<(pl.nimg + 127) / 128, 128, 0, st>>>(ctx->d_imgs, pl.nimg, ctx->self_scores));
@@ -1199,10 +1227,10 @@ static int eval_candidates_dev(snes_ctx *ctx, snes_image *const *images, int nim
     pl.d_scores = d_scores ? d_scores : ctx->scores;
     pl.with_self_error = with_error && ctx->fused == 3;
     pl.self_fresh = all_fresh(images, nimg);
+    pl.d_best = reinterpret_cast<Best *>(d_best);
+    pl.best_idx_base = cand_idx_base;
     RET(run_plan(ctx, cfg, pl));
-    if (d_best) {
-        LAUNCH(ctx, "k_argmin", k_argmin<<<nimg, 128, 0, ctx->stream>>>(pl.d_scores, ncand, cand_idx_base, reinterpret_cast<Best *>(d_best)));
-    }
+    ctx->maps_images.assign(images, images + nimg);
     return SNES_OK;
 }
 
@@ -1352,6 +1380,29 @@ extern "C" int snes_batch_step_tile_moves(snes_ctx *ctx, snes_image *const *imag
     return rc;
 }
 
+// Accept step + the optimize() that follows it (lib.rs:216-219 + 236-237, 280-281, 324-325).  When the candidates were
+// just evaluated by this context in full (every candidate of every image, maps still in the scratch buffer) and the images'
+// palette_maps were current, optimize() of an image that accepted a candidate is that candidate's map (k_adopt_map) and
+// optimize() of one that did not changes nothing; otherwise optimize() runs.
+static int ensure_ints(snes_ctx *ctx, size_t n);
+static int apply_and_optimize(snes_ctx *ctx, snes_image *const *images, int nimg, int slot, const uint8_t *d_cand_all, int ncand_all,
+                              const Best *d_best, int force) {
+    cudaStream_t st = ctx->stream;
+    const snes_config cfg = images[0]->cfg;
+    bool adopt = ctx->maps_live && ctx->maps_nimg == nimg && ctx->maps_ncand == ncand_all && ctx->maps_slot == slot &&
+                 ctx->maps_cand == d_cand_all && (int)ctx->maps_images.size() == nimg && all_fresh(images, nimg);
+    for (int j = 0; adopt && j < nimg; j++) adopt = ctx->maps_images[j] == images[j];
+    ctx->maps_live = false;
+    if (adopt) {
+        RET(ensure_ints(ctx, (size_t)nimg));
+        LAUNCH(ctx, "k_apply_best", k_apply_best<<<(nimg + 127) / 128, 128, 0, st>>>(ctx->d_imgs, nimg, slot, d_cand_all, ncand_all, d_best, force, ctx->d_ints));
+        LAUNCH(ctx, "k_adopt_map", k_adopt_map<<<dim3(64, nimg), 256, 0, st>>>(ctx->d_imgs, ctx->d_ints, ctx->maps, ncand_all, cfg.subpalette_size));
+        return SNES_OK;
+    }
+    LAUNCH(ctx, "k_apply_best", k_apply_best<<<(nimg + 127) / 128, 128, 0, st>>>(ctx->d_imgs, nimg, slot, d_cand_all, ncand_all, d_best, force));
+    return batch_optimize(ctx, images, nimg);
+}
+
 extern "C" int snes_merge_best_dev(snes_ctx *ctx, const snes_best *d_gathered, int nranks, int rank_stride, int nimg, snes_best *d_out) {
     if (!ctx || !d_gathered || !d_out || nranks < 1 || nimg < 1 || rank_stride < nimg) return fail(SNES_E_INVALID, "snes_merge_best_dev: bad argument");
     RET(set_device(ctx));
@@ -1366,9 +1417,8 @@ extern "C" int snes_batch_apply_best_dev(snes_ctx *ctx, snes_image *const *image
     const snes_config cfg = images[0]->cfg;
     RET(check_slot(cfg, palette, index));
     if (!d_cand_all || !d_best || ncand_all < 1) return fail(SNES_E_INVALID, "snes_batch_apply_best_dev: NULL argument");
-    LAUNCH(ctx, "k_apply_best", k_apply_best<<<(nimg + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_imgs, nimg, palette * cfg.subpalette_size + index, d_cand_all,
-                                                           ncand_all, reinterpret_cast<const Best *>(d_best), cfg.nes ? 1 : 0));
-    return batch_optimize(ctx, images, nimg);  // lib.rs:236-237, 280-281, 324-325
+    return apply_and_optimize(ctx, images, nimg, palette * cfg.subpalette_size + index, d_cand_all, ncand_all, reinterpret_cast<const Best *>(d_best),
+                              cfg.nes ? 1 : 0);
 }
 
 // One optimize_palette_entry_* call for every image of the batch.
@@ -1404,10 +1454,10 @@ static int batch_step(snes_ctx *ctx, snes_image *const *images, int nimg, int pa
     pl.d_scores = ctx->scores;
     pl.with_self_error = mode != 1 && ctx->fused == 3;
     pl.self_fresh = all_fresh(images, nimg);
+    pl.d_best = ctx->best;
     RET(run_plan(ctx, cfg, pl));
-    LAUNCH(ctx, "k_argmin", k_argmin<<<nimg, 128, 0, st>>>(ctx->scores, ncand, 0, ctx->best));
-    LAUNCH(ctx, "k_apply_best", k_apply_best<<<(nimg + 127) / 128, 128, 0, st>>>(ctx->d_imgs, nimg, slot, ctx->cand, ncand, ctx->best, mode == 1));
-    RET(batch_optimize(ctx, images, nimg));
+    ctx->maps_images.assign(images, images + nimg);
+    RET(apply_and_optimize(ctx, images, nimg, slot, ctx->cand, ncand, ctx->best, mode == 1));
     if (best) CK(cudaMemcpyAsync(best, ctx->best, sizeof(Best) * nimg, cudaMemcpyDeviceToHost, st));
     if (errors_after) {
         RET(batch_error(ctx, images, nimg));
@@ -1444,9 +1494,7 @@ extern "C" int snes_batch_step_random_shard_end(snes_ctx *ctx, snes_image *const
         return fail(SNES_E_INVALID, "snes_batch_step_random_shard_end: bad argument (or no _begin before it)");
     cudaStream_t st = ctx->stream;
     LAUNCH(ctx, "k_merge_best", k_merge_best<<<(nimg + 127) / 128, 128, 0, st>>>(reinterpret_cast<const Best *>(d_gathered), nranks, rank_stride, nimg, ctx->best));
-    LAUNCH(ctx, "k_apply_best", k_apply_best<<<(nimg + 127) / 128, 128, 0, st>>>(ctx->d_imgs, nimg, palette * cfg.subpalette_size + index, ctx->cand,
-                                                           ctx->shard_ncand_all, ctx->best, cfg.nes ? 1 : 0));
-    RET(batch_optimize(ctx, images, nimg));
+    RET(apply_and_optimize(ctx, images, nimg, palette * cfg.subpalette_size + index, ctx->cand, ctx->shard_ncand_all, ctx->best, cfg.nes ? 1 : 0));
     if (best) CK(cudaMemcpyAsync(best, ctx->best, sizeof(Best) * nimg, cudaMemcpyDeviceToHost, st));
     if (errors_after) {
         RET(batch_error(ctx, images, nimg));

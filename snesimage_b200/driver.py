@@ -135,6 +135,10 @@ class BatchOptimizer:
         self._best_local = torch.zeros(slots * 2, dtype=torch.int64, device=self.device)   # slots x 16 bytes
         self._best_all = torch.zeros(world * slots * 2, dtype=torch.int64, device=self.device)
         self._best = torch.zeros(slots * 2, dtype=torch.int64, device=self.device)
+        # a rank that owns its images outright (cand_ranks == 1) needs nobody's records to go on: its all-gather only
+        # publishes them, so it runs asynchronously on the process group's stream from one of two send buffers
+        self._send = [torch.zeros(slots * 2, dtype=torch.int64, device=self.device) for _ in range(2)]
+        self._pending = [None, None]
         # enqueue library work on torch's current stream so it orders with the collectives and is seen by
         # torch.cuda.Event timing; torch reports the legacy default stream as handle 0, which the C ABI reads as
         # "own stream", so name it explicitly (cudaStreamLegacy == 0x1)
@@ -154,6 +158,32 @@ class BatchOptimizer:
     def _exchange(self):
         """The step's one collective: all-gather of every rank's records (16 bytes per image slot)."""
         self.torch.distributed.all_gather_into_tensor(self._best_all, self._best_local, group=self.group)
+
+    def _owns_images(self) -> bool:
+        return self.plan.world > 1 and self.plan.cand_ranks == 1
+
+    def _send_buffer(self):
+        """The send buffer of this step; the collective that last read it (two steps ago) is ordered before its reuse."""
+        k = self.iteration & 1
+        if self._pending[k] is not None:
+            self._pending[k].wait()          # a stream-side wait, not a host one
+            self._pending[k] = None
+        return self._send[k]
+
+    def _publish(self, buf):
+        self._pending[self.iteration & 1] = self.torch.distributed.all_gather_into_tensor(self._best_all, buf, group=self.group, async_op=True)
+
+    def drain(self):
+        """Order every outstanding all-gather before whatever the current stream does next (e.g. reading gathered_records)."""
+        for k in (0, 1):
+            if self._pending[k] is not None:
+                self._pending[k].wait()
+                self._pending[k] = None
+
+    def gathered_records(self) -> np.ndarray:
+        """The whole job's winning records of the last step as every rank holds them after the all-gather: (world, slots)."""
+        self.drain()
+        return self._best_all.cpu().numpy().view(engine.BEST_DTYPE).reshape(self.plan.world, self.plan.slots)
 
     # ---- one optimize_palette_entry_random over the batch, device-resident inputs ----------------------
     def begin_step_dev(self, d_cand, ncand_total: int):
@@ -179,6 +209,17 @@ class BatchOptimizer:
     def step_random_dev(self, d_cand, ncand_total: int):
         """d_cand: uint8 CUDA tensor (local images, ncand_total, 3): the full candidate list of this rank's images,
         identical on the ranks of its group."""
+        if self._owns_images():
+            pl = self.plan
+            p, i = self.cursor.palette, self.cursor.palette_index
+            buf = self._send_buffer()
+            engine.batch_error_eval_candidates_slice_dev(self.images, p, i, d_cand.data_ptr(), ncand_total, 0, ncand_total, None, buf.data_ptr())
+            self._publish(buf)               # the NCCL exchange of the step, off the critical path
+            engine.batch_apply_best_dev(self.images, p, i, d_cand.data_ptr(), ncand_total, buf.data_ptr())
+            self.cursor.advance(self.config)
+            self.iteration += 1
+            self._best = buf
+            return
         self.begin_step_dev(d_cand, ncand_total)
         if self.plan.world > 1:
             self._exchange()
@@ -194,6 +235,12 @@ class BatchOptimizer:
         ncand_total = cand_host.shape[1]
         if pl.world == 1:
             best, _ = engine.batch_step_random(self.images, p, i, cand_host)
+        elif self._owns_images():
+            buf = self._send_buffer()
+            engine.batch_step_random_shard_begin(self.images, p, i, cand_host, 0, ncand_total, buf.data_ptr())
+            self._publish(buf)
+            best, _ = engine.batch_step_random_shard_end(self.images, p, i, buf.data_ptr(), 1, pl.slots, best_host)
+            self._best = buf
         else:
             lo, hi = shard_bounds(ncand_total, pl.slice, pl.cand_ranks)
             engine.batch_step_random_shard_begin(self.images, p, i, cand_host, lo, hi - lo, self._best_local.data_ptr())

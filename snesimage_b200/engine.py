@@ -88,6 +88,7 @@ _SIGNATURES = {
     "snes_ctx_set_chunk": (_i, [_vp, _i]),
     "snes_ctx_set_scorer": (_i, [_vp, _i, _i, _i]),
     "snes_ctx_profile_begin": (_i, [_vp]),
+    "snes_ctx_profile_only": (_i, [_vp, C.c_char_p]),
     "snes_ctx_profile_end": (_i, [_vp, _vp, _sz, C.POINTER(_sz)]),
     "snes_image_new": (_i, [_vp, _vp, _i, _i, C.POINTER(_Config), C.POINTER(_vp)]),
     "snes_image_free": (None, [_vp]),
@@ -212,7 +213,9 @@ class Context:
         """fused: 3 = k_score_v3 (default), 2 = k_score_v2 (its predecessor, kept as the A/B check)."""
         _check(self._l.snes_ctx_set_scorer(self._h, int(fused), int(block_width), int(delta_assign)), "snes_ctx_set_scorer")
 
-    def profile_begin(self):
+    def profile_begin(self, only: Optional[str] = None):
+        """Start per-launch CUDA-event timing; `only`: bracket just the launches whose kernel name contains it."""
+        _check(self._l.snes_ctx_profile_only(self._h, only.encode() if only else None), "snes_ctx_profile_only")
         _check(self._l.snes_ctx_profile_begin(self._h), "snes_ctx_profile_begin")
 
     def profile_end(self) -> dict:
