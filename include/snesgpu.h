@@ -92,6 +92,12 @@ int snes_ctx_profile_end(snes_ctx *ctx, char *buf, size_t cap, size_t *len);
  *   delta_assign != 0 without dithering, a candidate re-decides only the pixels its entry can change (default)
  * Env overrides at context creation: SNESGPU_FUSED, SNESGPU_DELTA. */
 int snes_ctx_set_scorer(snes_ctx *ctx, int fused, int block_width, int delta_assign);
+/* Replace the two 256-entry sRGB -> linear tables (index = 8-bit value): yuvxyb's transfer function, which feeds the
+ * SSIMULACRA2 planes, and palette's Srgb::into_linear, which feeds Lab.  NULL keeps / restores the built-in table (libm
+ * powf).  For pinning against tables dumped from the real crates (tests/golden/gen_reference_vectors.rs); call it before
+ * any image is created -- images keep the planes they were built with.  The tables live in constant memory: they are shared
+ * by every context of the process. */
+int snes_ctx_set_transfer_luts(snes_ctx *ctx, const float *yuvxyb_eotf /* 256 or NULL */, const float *palette_eotf /* 256 or NULL */);
 /* how many candidate evaluations have their scratch live at once (default 2048, env SNESGPU_CHUNK) */
 int snes_ctx_set_chunk(snes_ctx *ctx, int evaluations);
 

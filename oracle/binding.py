@@ -76,6 +76,8 @@ def lib():
         "ora_ciede2000_f32": (f, [_f32p, _f32p]),
         "ora_ciede2000_f64": (d, [_f64p, _f64p]),
         "ora_srgb_eotf": (f, [f]),
+        "ora_set_transfer_luts": (None, [vp, vp]),
+        "ora_get_transfer_luts": (None, [_f32p, _f32p]),
         "ora_cbrtf": (f, [f]),
         "ora_linear_rgb_to_xyb": (None, [_f32p, _f32p]),
         "ora_gaussian_coeffs": (None, [_f32p, _f32p, C.POINTER(C.c_int)]),
@@ -225,6 +227,19 @@ def kmeans(points, k):
     assign = np.zeros(len(pts), np.int32)
     it = lib().ora_kmeans(pts, len(pts), k, centres, assign)
     return it, centres, assign
+
+
+def set_transfer_luts(yuvxyb_eotf=None, palette_eotf=None):
+    """Swap in 256-entry sRGB -> linear tables dumped from the real crates (None: the built-in one, libm powf)."""
+    a = None if yuvxyb_eotf is None else np.ascontiguousarray(yuvxyb_eotf, np.float32).reshape(256)
+    b = None if palette_eotf is None else np.ascontiguousarray(palette_eotf, np.float32).reshape(256)
+    lib().ora_set_transfer_luts(None if a is None else a.ctypes.data, None if b is None else b.ctypes.data)
+
+
+def transfer_luts():
+    a, b = np.zeros(256, np.float32), np.zeros(256, np.float32)
+    lib().ora_get_transfer_luts(a, b)
+    return a, b
 
 
 def ciede2000_f64(l1, l2):

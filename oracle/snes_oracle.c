@@ -103,10 +103,36 @@ uint16_t ora_snes_as_u16(const uint8_t c5[3]) { /* lib.rs:679-681 */
 /* ============================================================================================ */
 /* palette 0.7.6 restated: Srgb<u8> -> Lab<D65,f32>, Lab<f64> -> Srgb<u8>, CIEDE2000              */
 /* ============================================================================================ */
+/* The two sRGB -> linear transfer functions only ever see 8-bit inputs on this path, so each is a 256-entry table.  The
+ * built-in tables come from the recalled formulas with libm's powf; ora_set_transfer_luts() swaps in tables dumped from the
+ * real crates (tests/golden/gen_reference_vectors.rs), which is how a maintainer with cargo pins this oracle. */
+static float g_lut_palette[256], g_lut_yuvxyb[256];
+static int g_luts_ready = 0;
+static float srgb_eotf_formula(float x);
+static void luts_init(void) {
+    if (g_luts_ready) return;
+    for (int v = 0; v < 256; v++) {
+        const float c = (float)v / 255.0f; /* into_format */
+        g_lut_palette[v] = c <= 0.04045f ? c / 12.92f : powf((c + 0.055f) / 1.055f, 2.4f); /* Srgb::into_linear */
+        g_lut_yuvxyb[v] = srgb_eotf_formula(c);
+    }
+    g_luts_ready = 1;
+}
+void ora_set_transfer_luts(const float *yuvxyb_eotf, const float *palette_eotf) {
+    g_luts_ready = 0;
+    luts_init();
+    if (yuvxyb_eotf) memcpy(g_lut_yuvxyb, yuvxyb_eotf, sizeof g_lut_yuvxyb);
+    if (palette_eotf) memcpy(g_lut_palette, palette_eotf, sizeof g_lut_palette);
+}
+void ora_get_transfer_luts(float *yuvxyb_eotf, float *palette_eotf) {
+    luts_init();
+    memcpy(yuvxyb_eotf, g_lut_yuvxyb, sizeof g_lut_yuvxyb);
+    memcpy(palette_eotf, g_lut_palette, sizeof g_lut_palette);
+}
+
 void ora_srgb8_to_lab_f32(uint8_t r8, uint8_t g8, uint8_t b8, float out[3]) {
-    float c[3] = {(float)r8 / 255.0f, (float)g8 / 255.0f, (float)b8 / 255.0f}; /* into_format */
-    for (int i = 0; i < 3; i++) /* Srgb::into_linear */
-        c[i] = c[i] <= 0.04045f ? c[i] / 12.92f : powf((c[i] + 0.055f) / 1.055f, 2.4f);
+    luts_init();
+    float c[3] = {g_lut_palette[r8], g_lut_palette[g8], g_lut_palette[b8]}; /* into_format + Srgb::into_linear */
     /* multiply_rgb_to_xyz: (m0*r + m1*g) + m2*b */
     float x = ((float)ORA_XYZ_M00 * c[0] + (float)ORA_XYZ_M01 * c[1]) + (float)ORA_XYZ_M02 * c[2];
     float y = ((float)ORA_XYZ_M10 * c[0] + (float)ORA_XYZ_M11 * c[1]) + (float)ORA_XYZ_M12 * c[2];
@@ -553,11 +579,12 @@ void ora_as_json_arrays(const ora_image *im, uint16_t *palette16, uint8_t *tiles
 /* ============================================================================================ */
 /* ssimulacra2 0.5.1 / yuvxyb 0.4.2 restated                                                      */
 /* ============================================================================================ */
-float ora_srgb_eotf(float x) { /* yuvxyb transfer: sRGB -> linear (zimg constants) */
+static float srgb_eotf_formula(float x) { /* yuvxyb transfer: sRGB -> linear (zimg constants) */
     x = x > 0.0f ? x : 0.0f;
     if (x < 12.92f * ORA_SRGB_BETA) return x / 12.92f;
     return powf((x + (ORA_SRGB_ALPHA - 1.0f)) / ORA_SRGB_ALPHA, 2.4f);
 }
+float ora_srgb_eotf(float x) { return srgb_eotf_formula(x); }
 
 float ora_cbrtf(float x) { /* FreeBSD msun s_cbrtf.c as ported by yuvxyb-math */
     const uint32_t B1 = 709958130u, B2 = 642849266u;
@@ -745,9 +772,10 @@ typedef struct {
 } linrgb_t;
 
 static linrgb_t lin_from_rgba8(const uint8_t *rgba, int w, int h) { /* lib.rs:506-516 + yuvxyb Rgb->LinearRgb */
+    luts_init();
     linrgb_t o = {w, h, (float *)malloc(sizeof(float) * 3 * (size_t)w * h)};
     for (size_t i = 0; i < (size_t)w * h; i++)
-        for (int c = 0; c < 3; c++) o.d[3 * i + c] = ora_srgb_eotf((float)rgba[4 * i + c] / 255.0f);
+        for (int c = 0; c < 3; c++) o.d[3 * i + c] = g_lut_yuvxyb[rgba[4 * i + c]]; /* ora_srgb_eotf(v / 255) unless a table was injected */
     return o;
 }
 

@@ -81,6 +81,9 @@ void ora_lab_f64_to_srgb8(const double lab[3], uint8_t out[3]);             /* p
 float ora_ciede2000_f32(const float lab1[3], const float lab2[3]);          /* palette: Ciede2000 */
 double ora_ciede2000_f64(const double lab1[3], const double lab2[3]);       /* same formula in f64 (KAT) */
 float ora_srgb_eotf(float v);                                               /* yuvxyb sRGB -> linear */
+/* the two 256-entry sRGB -> linear tables the path uses (index = 8-bit value): yuvxyb's and palette's; NULL keeps the built-in one */
+void ora_set_transfer_luts(const float *yuvxyb_eotf, const float *palette_eotf);
+void ora_get_transfer_luts(float *yuvxyb_eotf, float *palette_eotf);
 float ora_cbrtf(float x);                                                   /* yuvxyb-math cbrtf (FreeBSD msun) */
 void ora_linear_rgb_to_xyb(const float rgb[3], float xyb[3]);               /* yuvxyb, before make_positive */
 void ora_gaussian_coeffs(float n2[3], float d1[3], int *radius);            /* libjxl CreateRecursiveGaussian(1.5) */

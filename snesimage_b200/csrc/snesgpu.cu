@@ -437,6 +437,26 @@ extern "C" int snes_ctx_synchronize(snes_ctx *ctx) {
     return SNES_OK;
 }
 
+// The two 256-entry sRGB -> linear tables are the only place where the third-party transfer functions enter the GPU path
+// (yuvxyb's for the SSIMULACRA2 planes, palette's for Lab).  The built-in ones come from libm's powf; a maintainer who can
+// build the crates dumps theirs (tests/golden/gen_reference_vectors.rs) and swaps them in here -- no kernel changes.
+extern "C" int snes_ctx_set_transfer_luts(snes_ctx *ctx, const float *yuvxyb_eotf, const float *palette_eotf) {
+    if (!ctx) return fail(SNES_E_INVALID, "ctx is NULL");
+    RET(set_device(ctx));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float lut[256], lut2[256];
+    for (int v = 0; v < 256; v++) {
+        lut[v] = yuvxyb_eotf ? yuvxyb_eotf[v] : srgb_eotf_yuvxyb((float)v / 255.0f);
+        const float c = (float)v / 255.0f;
+        lut2[v] = palette_eotf ? palette_eotf[v] : (c <= 0.04045f ? c / 12.92f : powf((c + 0.055f) / 1.055f, 2.4f));
+    }
+    CK(cudaMemcpyToSymbol(c_lin_lut, lut, sizeof(lut)));
+    CK(cudaMemcpyToSymbol(c_srgb_lin_lut, lut2, sizeof(lut2)));
+    LAUNCH(ctx, "k_build_lab_table", k_build_lab_table<<<128, 256, 0, ctx->stream>>>(ctx->labtab));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SNES_OK;
+}
+
 extern "C" int snes_ctx_profile_only(snes_ctx *ctx, const char *name_part) {
     if (!ctx) return fail(SNES_E_INVALID, "ctx is NULL");
     ctx->prof_filter = name_part ? name_part : "";

@@ -86,6 +86,7 @@ _SIGNATURES = {
     "snes_ctx_set_stream": (_i, [_vp, _vp]),
     "snes_ctx_synchronize": (_i, [_vp]),
     "snes_ctx_set_chunk": (_i, [_vp, _i]),
+    "snes_ctx_set_transfer_luts": (_i, [_vp, _vp, _vp]),
     "snes_ctx_set_scorer": (_i, [_vp, _i, _i, _i]),
     "snes_ctx_profile_begin": (_i, [_vp]),
     "snes_ctx_profile_only": (_i, [_vp, C.c_char_p]),
@@ -208,6 +209,12 @@ class Context:
 
     def set_chunk(self, evaluations: int):
         _check(self._l.snes_ctx_set_chunk(self._h, int(evaluations)), "snes_ctx_set_chunk")
+
+    def set_transfer_luts(self, yuvxyb_eotf=None, palette_eotf=None):
+        """Swap in verified 256-entry sRGB -> linear tables (None: the built-in one).  Before any image is created."""
+        a = None if yuvxyb_eotf is None else np.ascontiguousarray(yuvxyb_eotf, np.float32).reshape(256)
+        b = None if palette_eotf is None else np.ascontiguousarray(palette_eotf, np.float32).reshape(256)
+        _check(self._l.snes_ctx_set_transfer_luts(self._h, _ptr(a), _ptr(b)), "snes_ctx_set_transfer_luts")
 
     def set_scorer(self, fused: int = 3, block_width: int = 32, delta_assign: bool = True):
         """fused: 3 = k_score_v3 (default), 2 = k_score_v2 (its predecessor, kept as the A/B check)."""
