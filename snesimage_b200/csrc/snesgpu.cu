@@ -654,7 +654,7 @@ static int launch_scorer(snes_ctx *ctx, const FusedArgs &fa, int ec, const Fused
         else va.tm2 = va.tm;
         va.counter = ctx->v3_counter;
         va.hscratch = ctx->v3_scratch;
-        const int items = 2 * (va.nitems + va.nitems2);   // every (evaluation, channel) is two work items
+        const int items = V3_PARTS * (va.nitems + va.nitems2);   // work items per (evaluation, channel): see k_score_v3
         const int grid = items < ctx->nsm * V3_CTAS_PER_SM ? items : ctx->nsm * V3_CTAS_PER_SM;
         CK(cudaMemsetAsync(ctx->v3_counter, 0, sizeof(int), st));
         LAUNCH(ctx, "k_score_v3", k_score_v3<<<grid, V3_THREADS, sizeof(V3Smem), st>>>(va));
