@@ -41,7 +41,7 @@ def scorer_source_hash() -> str:
     file's DRAM traffic only while it still describes the kernel in the tree."""
     import hashlib
     h = hashlib.sha256()
-    for f in ("common.cuh", "kernels.cuh", "score_common.cuh", "score_v2.cuh", "score_v3.cuh"):
+    for f in ("common.cuh", "score_common.cuh", "score_v2.cuh", "score_v3.cuh"):
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()
