@@ -10,8 +10,7 @@ step is the all-gather of the 16-byte (error, index) records over NCCL.
 
   value     whole-job candidate evaluations / s, candidate lists resident in HBM (device-timed, max over ranks)
   e2e       the same step through the host-buffer entry points of the C ABI: candidate H2D + winning records D2H inside
-            every call (N = 1: snes_batch_step_random; N > 1: snes_batch_step_random_shard_begin / _end around the
-            all-gather)
+            every call (N = 1: snes_batch_step_random; N > 1: snes_dist_step_random, the all-gather inside the library)
   roofline  the dominant kernel's algorithmic bytes / its CUDA-event time, against MEASURED_PEAKS.json
   cpu_baseline  the CPU oracle (C restatement of the reference) on this box's host cores, bounded sample
   outside the headline's timed region: `weak` and `candidate_sharded` (N > 1), `modes` and `configs` (N = 1)
@@ -327,6 +326,10 @@ def run_ours(args):
     value = evals_per_step * args.steps / (ms * 1e-3)
 
     # ---- host-buffer arm (e2e): the same steps again from pinned host memory through the C ABI's host entry points ----
+    if world > 1:
+        from snesimage_b200 import driver
+        driver.init_library_comm(ctx, rank, world)     # the library's own NCCL communicator: the sharded step is ONE C call
+        job.opt.library_comm = True
     for it in range(min(3, args.warmup)):
         job.step_host(it)
     ms_e2e = timed(job.step_host, range(args.warmup, nsteps))
@@ -422,7 +425,7 @@ def run_ours(args):
             "config": build_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                    "entry_points": "snes_batch_step_random" if world == 1 else "snes_batch_step_random_shard_begin + all_gather + snes_batch_step_random_shard_end"},
+                    "entry_points": "snes_batch_step_random" if world == 1 else "snes_dist_step_random (one call per rank and step: H2D, error + candidates, ncclAllGather inside the library, merge, accept, optimize, D2H)"},
             "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "sharding": {"plan": plan_text, "images_per_rank": nloc,
                          "state_checksums": [{"rank": r, "image_group": g, "fnv1a64": c} for r, g, c in sums],

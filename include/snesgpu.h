@@ -198,6 +198,26 @@ int snes_batch_step_random_shard_end(snes_ctx *ctx, snes_image *const *images, i
                                      const snes_best *d_gathered, int nranks, int rank_stride, snes_best *best,
                                      double *errors_after);
 
+/* ---- the same sharded step with the collective INSIDE the library: one call, host buffers in and out ---------------------
+ * For hosts without a process-group library of their own (the reference is Rust).  NCCL is loaded at run time (libnccl.so.2).
+ *   snes_comm_unique_id   on one rank: a 128-byte NCCL unique id, to be handed to every rank by any means
+ *   snes_ctx_comm_init    on every rank (collective): the context's communicator over `world` ranks
+ *   snes_dist_plan        which images of a job of nimg_total images a rank holds -- [img_lo, img_hi) -- and how its group slices
+ *                         the candidates: as many image groups as divide the world and do not exceed nimg_total; the ranks of
+ *                         a group (cand_ranks of them, this one being `slice`) hold replicas and split the candidate list;
+ *                         slots = records per rank in the all-gather (the largest group)
+ *   snes_dist_step_random optimize_palette_entry_random (lib.rs:191-240) for this rank's images as a member of the job: cand
+ *                         (host, nimg_local * ncand * 3: the FULL lists of its images, identical on the ranks of its group) ->
+ *                         error() + its slice of the candidates -> ncclAllGather of the records on the context's stream ->
+ *                         merge over its group, accept, optimize().  best[nimg_local] (host, optional): the winning records;
+ *                         all_best[world * slots] (host, optional): every rank's records as gathered.  Synchronous. */
+int snes_comm_unique_id(uint8_t *out128);
+int snes_ctx_comm_init(snes_ctx *ctx, const uint8_t *id128, int rank, int world);
+int snes_ctx_comm_destroy(snes_ctx *ctx);
+int snes_dist_plan(int nimg_total, int rank, int world, int *img_lo, int *img_hi, int *cand_ranks, int *slice, int *slots);
+int snes_dist_step_random(snes_ctx *ctx, snes_image *const *images, int nimg_local, int nimg_total, int palette, int index,
+                          const uint8_t *cand, int ncand, snes_best *best, snes_best *all_best);
+
 /* optimize_palette_entry_nes / _channel for every image of a batch (lib.rs:242-284, 286-328) */
 int snes_batch_step_nes(snes_ctx *ctx, snes_image *const *images, int nimg, int palette, int index, snes_best *best,
                         double *errors_after);

@@ -17,7 +17,7 @@ HEADERS = ["common.cuh", "kernels.cuh", "lab.cuh", "dither.cuh", "kmeans.cuh", "
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-shared", "-ldl",
 ]
 
 

@@ -6,6 +6,8 @@
 // is no CPU fallback -- without a usable sm_100 device every compute entry point returns SNES_E_CUDA.
 #include "../../include/snesgpu.h"
 
+#include <dlfcn.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -91,6 +93,10 @@ struct snes_ctx {
     int maps_nimg = 0, maps_ncand = 0, maps_slot = -1;   // full candidate lists): [maps_nimg][maps_ncand][NPIX]
     const uint8_t *maps_cand = nullptr;
     std::vector<snes_image *> maps_images;
+    void *nccl_comm = nullptr; // ncclComm_t of snes_ctx_comm_init (the library's own communicator, NCCL loaded at run time)
+    int comm_rank = 0, comm_world = 1;
+    Best *d_send = nullptr, *d_gather = nullptr;   // [slots], [world * slots] records of snes_dist_step_random
+    size_t dist_cap = 0;
     int shard_ncand_all = 0;   // candidates per image of the list snes_batch_step_random_shard_begin left in `cand`
 
     float4 *labtab = nullptr;  // BGR555 -> Lab<D65,f32>
@@ -402,6 +408,9 @@ extern "C" void snes_ctx_destroy(snes_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_scratch(ctx);
+    snes_ctx_comm_destroy(ctx);
+    cudaFree(ctx->d_send);
+    cudaFree(ctx->d_gather);
     cudaFree(ctx->labtab);
     cudaFree(ctx->d_ints);
     cudaFree(ctx->best_m);
@@ -1520,6 +1529,149 @@ extern "C" int snes_batch_step_random_shard_end(snes_ctx *ctx, snes_image *const
         RET(batch_error(ctx, images, nimg));
         CK(cudaMemcpyAsync(errors_after, ctx->self_scores, sizeof(double) * nimg, cudaMemcpyDeviceToHost, st));
     }
+    CK(cudaStreamSynchronize(st));
+    return SNES_OK;
+}
+
+// ---- the sharded step with the collective inside the library -------------------------------------------------------------
+// NCCL is loaded at run time (dlopen "libnccl.so.2": the copy a host process already holds -- torch's -- or the system's), so
+// the library has no link-time dependency on it and loads on a box without NCCL.  The unique id travels through the ABI: the
+// host creates it on one rank and hands it to the others by whatever means it has (a Rust host: a file, a socket, MPI).
+struct snes_nccl_id {
+    char internal[128];
+};
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(snes_nccl_id *) = nullptr;
+    int (*CommInitRank)(void **, int, snes_nccl_id, int) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi *nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) {
+            api.GetUniqueId = (int (*)(snes_nccl_id *))dlsym(h, "ncclGetUniqueId");
+            api.CommInitRank = (int (*)(void **, int, snes_nccl_id, int))dlsym(h, "ncclCommInitRank");
+            api.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))dlsym(h, "ncclAllGather");
+            api.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
+            api.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+            if (api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy) api.lib = h;
+        }
+    }
+    return api.lib ? &api : nullptr;
+}
+static int nccl_fail(NcclApi *api, const char *what, int rc) {
+    return fail(SNES_E_CUDA, std::string(what) + ": " + (api && api->GetErrorString ? api->GetErrorString(rc) : "NCCL error") + " (" + std::to_string(rc) + ")");
+}
+
+extern "C" int snes_comm_unique_id(uint8_t *out128) {
+    if (!out128) return fail(SNES_E_INVALID, "snes_comm_unique_id: NULL argument");
+    NcclApi *api = nccl_api();
+    if (!api) return fail(SNES_E_CUDA, "libnccl.so.2 could not be loaded");
+    snes_nccl_id id;
+    const int rc = api->GetUniqueId(&id);
+    if (rc != 0) return nccl_fail(api, "ncclGetUniqueId", rc);
+    memcpy(out128, id.internal, 128);
+    return SNES_OK;
+}
+
+extern "C" int snes_ctx_comm_init(snes_ctx *ctx, const uint8_t *id128, int rank, int world) {
+    if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return fail(SNES_E_INVALID, "snes_ctx_comm_init: bad argument");
+    NcclApi *api = nccl_api();
+    if (!api) return fail(SNES_E_CUDA, "libnccl.so.2 could not be loaded");
+    RET(set_device(ctx));
+    snes_ctx_comm_destroy(ctx);
+    snes_nccl_id id;
+    memcpy(id.internal, id128, 128);
+    void *comm = nullptr;
+    const int rc = api->CommInitRank(&comm, world, id, rank);
+    if (rc != 0) return nccl_fail(api, "ncclCommInitRank", rc);
+    ctx->nccl_comm = comm;
+    ctx->comm_rank = rank;
+    ctx->comm_world = world;
+    return SNES_OK;
+}
+
+extern "C" int snes_ctx_comm_destroy(snes_ctx *ctx) {
+    if (!ctx) return fail(SNES_E_INVALID, "ctx is NULL");
+    if (ctx->nccl_comm) {
+        NcclApi *api = nccl_api();
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        if (api) api->CommDestroy(ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+    }
+    ctx->comm_rank = 0;
+    ctx->comm_world = 1;
+    return SNES_OK;
+}
+
+// driver.plan_shards in C: image groups x candidate slices.  As many groups as divide the world and do not exceed the number of
+// images; the ranks of a group slice the candidates.
+extern "C" int snes_dist_plan(int nimg_total, int rank, int world, int *img_lo, int *img_hi, int *cand_ranks, int *slice, int *slots) {
+    if (nimg_total < 1 || world < 1 || rank < 0 || rank >= world) return fail(SNES_E_INVALID, "snes_dist_plan: bad argument");
+    int groups = 1;
+    for (int d = 1; d <= world; d++)
+        if (world % d == 0 && d <= nimg_total) groups = d;
+    const int cr = world / groups, g = rank / cr;
+    if (img_lo) *img_lo = (int)(((long long)g * nimg_total) / groups);
+    if (img_hi) *img_hi = (int)(((long long)(g + 1) * nimg_total) / groups);
+    if (cand_ranks) *cand_ranks = cr;
+    if (slice) *slice = rank % cr;
+    if (slots) *slots = (nimg_total + groups - 1) / groups;
+    return SNES_OK;
+}
+
+extern "C" int snes_dist_step_random(snes_ctx *ctx, snes_image *const *images, int nimg_local, int nimg_total, int palette, int index,
+                                     const uint8_t *cand, int ncand, snes_best *best, snes_best *all_best) {
+    RET(bind_images(ctx, images, nimg_local));
+    const snes_config cfg = images[0]->cfg;
+    RET(check_slot(cfg, palette, index));
+    if (!cand || ncand < 1) return fail(SNES_E_INVALID, "snes_dist_step_random: no candidates");
+    const int world = ctx->comm_world, rank = ctx->comm_rank;
+    if (world > 1 && !ctx->nccl_comm) return fail(SNES_E_INVALID, "snes_dist_step_random: no communicator (snes_ctx_comm_init)");
+    int lo_img, hi_img, cr, slice, slots;
+    RET(snes_dist_plan(nimg_total, rank, world, &lo_img, &hi_img, &cr, &slice, &slots));
+    if (hi_img - lo_img != nimg_local) return fail(SNES_E_INVALID, "snes_dist_step_random: this rank must hold images [" + std::to_string(lo_img) + ", " +
+                                                                       std::to_string(hi_img) + ") of the job (snes_dist_plan)");
+    const size_t E = (size_t)nimg_local * ncand;
+    for (size_t i = 0; i < E * 3; i++)
+        if (cand[i] > 32) return fail(SNES_E_INVALID, "colour component > 32");
+    RET(ensure_evals(ctx, E));
+    if ((size_t)world * slots > ctx->dist_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_send);
+        cudaFree(ctx->d_gather);
+        ctx->d_send = ctx->d_gather = nullptr;
+        ctx->dist_cap = 0;
+        RET(dev_alloc(&ctx->d_send, (size_t)slots));
+        RET(dev_alloc(&ctx->d_gather, (size_t)world * slots));
+        ctx->dist_cap = (size_t)world * slots;
+    }
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->cand, cand, E * 3, cudaMemcpyHostToDevice, st));
+    LAUNCH(ctx, "k_no_best", k_no_best<<<(slots + 127) / 128, 128, 0, st>>>(ctx->d_send, slots));   // padding slots of a smaller group
+    const int lo = (int)(((long long)slice * ncand) / cr), hi = (int)(((long long)(slice + 1) * ncand) / cr);
+    RET(eval_candidates_dev(ctx, images, nimg_local, palette, index, ctx->cand, hi - lo, lo, nullptr, reinterpret_cast<snes_best *>(ctx->d_send), true, ncand, lo));
+    const Best *mine = ctx->d_send;
+    int nranks = 1, stride = slots;
+    if (world > 1) {
+        NcclApi *api = nccl_api();
+        const int rc = api->AllGather(ctx->d_send, ctx->d_gather, (size_t)slots * sizeof(Best), /* ncclChar */ 0, ctx->nccl_comm, st);
+        if (rc != 0) return nccl_fail(api, "ncclAllGather", rc);
+        mine = ctx->d_gather + (size_t)(rank - slice) * slots;   // the records of this rank's group: cr consecutive ranks
+        nranks = cr;
+    }
+    LAUNCH(ctx, "k_merge_best", k_merge_best<<<(nimg_local + 127) / 128, 128, 0, st>>>(mine, nranks, stride, nimg_local, ctx->best));
+    RET(apply_and_optimize(ctx, images, nimg_local, palette * cfg.subpalette_size + index, ctx->cand, ncand, ctx->best, cfg.nes ? 1 : 0));
+    if (best) CK(cudaMemcpyAsync(best, ctx->best, sizeof(Best) * nimg_local, cudaMemcpyDeviceToHost, st));
+    if (all_best) CK(cudaMemcpyAsync(all_best, world > 1 ? ctx->d_gather : ctx->d_send, sizeof(Best) * (size_t)world * slots, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return SNES_OK;
 }

@@ -101,6 +101,17 @@ def plan_shards(nimg: int, rank: int, world: int, mode: str = "hybrid") -> Shard
     return ShardPlan(nimg, rank, world, groups, cand_ranks, group, sl, lo, hi, -(-nimg // groups))
 
 
+def init_library_comm(ctx: engine.Context, rank: int, world: int, group=None):
+    """Give the library its own NCCL communicator over the ranks of `group`: rank 0 makes the unique id (snes_comm_unique_id),
+    the process group hands it round, every rank joins (snes_ctx_comm_init).  After this snes_dist_step_random runs a whole
+    sharded step, all-gather included, in one C call -- what a host without torch (the reference is Rust) would use."""
+    import torch.distributed as dist
+    box = [engine.comm_unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0, group=group)
+    ctx.comm_init(box[0], rank, world)
+
+
 def merge_best_host(gathered: np.ndarray) -> np.ndarray:
     """Host restatement of k_merge_best for the gloo tests: gathered is (R, nimg) of BEST_DTYPE with
     global candidate indices; returns the lexicographic minimum of (err, idx) per image."""
@@ -139,6 +150,7 @@ class BatchOptimizer:
         # publishes them, so it runs asynchronously on the process group's stream from one of two send buffers
         self._send = [torch.zeros(slots * 2, dtype=torch.int64, device=self.device) for _ in range(2)]
         self._pending = [None, None]
+        self.library_comm = False    # step_random_host through snes_dist_step_random (after init_library_comm)
         # enqueue library work on torch's current stream so it orders with the collectives and is seen by
         # torch.cuda.Event timing; torch reports the legacy default stream as handle 0, which the C ABI reads as
         # "own stream", so name it explicitly (cudaStreamLegacy == 0x1)
@@ -235,6 +247,9 @@ class BatchOptimizer:
         ncand_total = cand_host.shape[1]
         if pl.world == 1:
             best, _ = engine.batch_step_random(self.images, p, i, cand_host)
+        elif self.library_comm:
+            # one C call: candidate H2D, error() + this rank's share, ncclAllGather inside the library, merge, accept, optimize()
+            best, _ = engine.dist_step_random(self.images, pl.nimg, p, i, cand_host)
         elif self._owns_images():
             buf = self._send_buffer()
             engine.batch_step_random_shard_begin(self.images, p, i, cand_host, 0, ncand_total, buf.data_ptr())

@@ -120,6 +120,11 @@ _SIGNATURES = {
     "snes_batch_step_random_shard_begin": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "snes_batch_step_random_shard_end": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "snes_image_state_checksum": (_i, [_vp, C.POINTER(C.c_uint64)]),
+    "snes_comm_unique_id": (_i, [_vp]),
+    "snes_ctx_comm_init": (_i, [_vp, _vp, _i, _i]),
+    "snes_ctx_comm_destroy": (_i, [_vp]),
+    "snes_dist_plan": (_i, [_i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "snes_dist_step_random": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "snes_batch_eval_candidates_multi": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp]),
     "snes_image_iterate": (_i, [_vp, _i, _vp, _i, _vp, _i, C.POINTER(_i), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "snes_batch_apply_best_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
@@ -209,6 +214,14 @@ class Context:
 
     def set_chunk(self, evaluations: int):
         _check(self._l.snes_ctx_set_chunk(self._h, int(evaluations)), "snes_ctx_set_chunk")
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """The library's own NCCL communicator (collective: every rank calls it with the id rank 0 got from comm_unique_id)."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(self._l.snes_ctx_comm_init(self._h, buf, int(rank), int(world)), "snes_ctx_comm_init")
+
+    def comm_destroy(self):
+        _check(self._l.snes_ctx_comm_destroy(self._h), "snes_ctx_comm_destroy")
 
     def set_transfer_luts(self, yuvxyb_eotf=None, palette_eotf=None):
         """Swap in verified 256-entry sRGB -> linear tables (None: the built-in one).  Before any image is created."""
@@ -592,6 +605,33 @@ def batch_step_random_shard_end(images: Sequence[OptimizedImage], palette: int, 
     _check(ctx._l.snes_batch_step_random_shard_end(ctx._h, _handles(images), nimg, palette, index, d_gathered, nranks, rank_stride,
                                                    _ptr(best), _ptr(errs)), "snes_batch_step_random_shard_end")
     return best, errs
+
+
+def comm_unique_id() -> bytes:
+    """A 128-byte NCCL unique id (call on one rank, hand the bytes to the others)."""
+    buf = (C.c_uint8 * 128)()
+    _check(lib().snes_comm_unique_id(buf), "snes_comm_unique_id")
+    return bytes(buf)
+
+
+def dist_plan(nimg_total: int, rank: int, world: int) -> dict:
+    """snes_dist_plan: the library's own statement of driver.plan_shards."""
+    v = [_i(0) for _ in range(5)]
+    _check(lib().snes_dist_plan(int(nimg_total), int(rank), int(world), *[C.byref(x) for x in v]), "snes_dist_plan")
+    return dict(zip(("img_lo", "img_hi", "cand_ranks", "slice", "slots"), (int(x.value) for x in v)))
+
+
+def dist_step_random(images: Sequence[OptimizedImage], nimg_total: int, palette: int, index: int, cand, world_slots: int = 0):
+    """One sharded optimize_palette_entry_random with the all-gather inside the library (snes_dist_step_random).
+    cand: (local images, ncand, 3).  Returns (winning records of the local images, every rank's records or None)."""
+    ctx = _ctx_of(images)
+    nimg = len(images)
+    cand = _u8(cand).reshape(nimg, -1, 3)
+    best = np.zeros(nimg, BEST_DTYPE)
+    allb = np.zeros(world_slots, BEST_DTYPE) if world_slots else None
+    _check(ctx._l.snes_dist_step_random(ctx._h, _handles(images), nimg, int(nimg_total), palette, index, _ptr(cand), cand.shape[1],
+                                        _ptr(best), _ptr(allb)), "snes_dist_step_random")
+    return best, allb
 
 
 def batch_apply_best_dev(images: Sequence[OptimizedImage], palette: int, index: int, d_cand_all: int, ncand_all: int, d_best: int):

@@ -81,6 +81,17 @@ def test_plan_shards_covers_every_image_and_candidate_once():
         driver.plan_shards(4, 2, 2)
 
 
+def test_library_plan_equals_driver_plan():
+    """snes_dist_plan (the C restatement a torch-free host uses) and driver.plan_shards name the same images, slices and slots."""
+    for nimg in (1, 3, 4, 5, 7, 64):
+        for world in (1, 2, 3, 4, 6, 8):
+            for r in range(world):
+                a, p = engine.dist_plan(nimg, r, world), driver.plan_shards(nimg, r, world)
+                assert (a["img_lo"], a["img_hi"], a["cand_ranks"], a["slice"], a["slots"]) == (p.img_lo, p.img_hi, p.cand_ranks, p.slice, p.slots)
+    with pytest.raises(engine.SnesGpuError):
+        engine.dist_plan(4, 2, 2)
+
+
 def test_bench_relaunch_keeps_the_json_line_on_stdout(tmp_path):
     """`python bench.py --gpus N` outside torchrun relaunches itself under torch.distributed.run; the child must inherit the
     real stdout (the parent used to point fd 1 at stderr first, so the line went to stderr).  A stub stands in

@@ -36,6 +36,9 @@ def _job(rank, world, port, nimg, mode, out):
     engine.batch_initialize_tiles(ims)
     engine.batch_recalculate_palettes(ims)
     opt = driver.BatchOptimizer(ctx, ims, plan=plan, seed=11)
+    if world > 1 and mode == "hybrid":       # the host-buffer steps through the library's own communicator (one C call)
+        driver.init_library_comm(ctx, rank, world)
+        opt.library_comm = True
     records = []
     for it in range(STEPS):
         cand = opt.candidates_host(NCAND)
