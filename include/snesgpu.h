@@ -98,6 +98,11 @@ int snes_ctx_set_scorer(snes_ctx *ctx, int fused, int block_width, int delta_ass
  * any image is created -- images keep the planes they were built with.  The tables live in constant memory: they are shared
  * by every context of the process. */
 int snes_ctx_set_transfer_luts(snes_ctx *ctx, const float *yuvxyb_eotf /* 256 or NULL */, const float *palette_eotf /* 256 or NULL */);
+/* SSIMULACRA2's pooling table gives weight 0.0 to both ssim_map numbers of (channel X, scale 0) and of (channel B, scale 0);
+ * k_score_v3 therefore computes only edge_diff_map there (one blurred plane per channel instead of three), decided from the table
+ * itself at context creation.  on != 0: compute every term everywhere (A/B check: error() must not change by a bit). Env:
+ * SNESGPU_ALL_TERMS=1. */
+int snes_ctx_set_all_terms(snes_ctx *ctx, int on);
 /* how many candidate evaluations have their scratch live at once (default 2048, env SNESGPU_CHUNK) */
 int snes_ctx_set_chunk(snes_ctx *ctx, int evaluations);
 

@@ -58,7 +58,9 @@ struct ImgDev {
     const float *xyb_cm;      // same, transposed [scale][ch][x][y]
     float *mu1;               // blur(i1)       [scale][ch][y][x]
     float *s11;               // blur(i1*i1)    [scale][ch][y][x]
-    float2 *ms11;             // (mu1, s11) interleaved, same index space (read by k_score_v2's maps)
+    float2 *ms11;             // (mu1, s11) interleaved, same index space (read by the scorers' maps)
+    float2 *bfxb;             // scale 0 only, [y][x]: (|i1 - mu1| of channel X, of channel B): the source side of edge_diff_map
+                              // for the two channels whose ssim_map carries no weight at scale 0 (score_v3.cuh: v3_scale0_pair)
     PalTables *tables;
     double *cur_err;          // error() of the current state
     const float *lab;         // per-pixel Lab of the original (perceptual mode), [NPIX][4]

@@ -34,6 +34,12 @@ __device__ __forceinline__ void cp_async16(unsigned sdst, const void *gsrc) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 __device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
+// bfxb[px] = (|i1 - mu1| of X, |i1 - mu1| of B) at scale 0: the same f32 expression the maps evaluate per pixel.  grid 256 x 256.
+__global__ void __launch_bounds__(256) k_make_bfxb(ImgDev im) {
+    const int px = blockIdx.x * 256 + threadIdx.x;
+    im.bfxb[px] = make_float2(fabsf(im.xyb_rm[px] - im.mu1[px]), fabsf(im.xyb_rm[2 * NPIX + px] - im.mu1[2 * NPIX + px]));
+}
+
 // Msssim::score of ssimulacra2 (108-weight pooling, cubic, power) and error() = 100 - score (lib.rs:547) for one
 // evaluation's partial sums pe[scale][channel][6], by one warp: lane q < 18 prepares the six terms of (channel q / 6, scale
 // q % 6) -- the loads and the fourth roots, which is where a single thread spent its time -- and every lane then runs the

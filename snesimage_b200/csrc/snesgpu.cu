@@ -64,6 +64,7 @@ struct snes_ctx {
     float *v3_scratch = nullptr;
     float *self_xyb = nullptr;        // [img_cap][EVAL_XYB_FLOATS] coarse pyramid of the images' own state (fused error + candidates)
     double *self_partials = nullptr;  // [img_cap][NSCALES*3*NSUMS]
+    int pair_xb = 0;  // scale 0 of channels X and B carries no ssim_map weight in the pooling table: edge-only pair items (score_v3.cuh)
     int delta = 1;    // 1: no-dither candidates re-decide only the pixels the replaced entry can change (SNESGPU_DELTA)
 
     // per-chunk scratch
@@ -294,6 +295,11 @@ static const uint8_t kNes[NES_COUNT][3] = {  // lib.rs:687-742
     {8, 24, 24},  {9, 9, 9},    {31, 31, 31}, {25, 29, 31}, {27, 27, 31}, {29, 27, 31}, {31, 26, 31}, {31, 26, 30},
     {31, 27, 25}, {31, 28, 22}, {30, 30, 21}, {27, 31, 21}, {25, 31, 23}, {24, 31, 26}, {24, 30, 30}, {23, 24, 23}};
 
+static int weights_allow_pair_xb() {
+    return kWeights[(0 * 6 + 0) * 6 + 0] == 0.0 && kWeights[(0 * 6 + 0) * 6 + 3] == 0.0 && kWeights[(2 * 6 + 0) * 6 + 0] == 0.0 &&
+           kWeights[(2 * 6 + 0) * 6 + 3] == 0.0;
+}
+
 static constexpr int kBlurHSmem = 4 * 2 * 32 * 33 * (int)sizeof(float);
 
 static int ctx_init(snes_ctx *ctx, int nsm);
@@ -368,6 +374,12 @@ static int ctx_init(snes_ctx *ctx, int nsm) {
         CK(cudaMemcpyToSymbol(c_m1p, &m1p, sizeof(m1p)));
     }
     CK(cudaMemcpyToSymbol(c_weight, kWeights, sizeof(kWeights)));
+    // weights of (channel c, scale s): kWeights[(c * 6 + s) * 6 + {0: ssim mean, 1: artifact mean, 2: detail mean, 3: ssim 4-norm, ...}].
+    // ssim_map of a (channel, scale) whose two ssim weights are exactly zero cannot change the score; the scorer then skips the two
+    // blur planes only ssim_map needs.  Decided from the table itself, so a corrected table changes the decision with it.
+    ctx->pair_xb = weights_allow_pair_xb();
+    if (const char *c = getenv("SNESGPU_ALL_TERMS"))
+        if (atoi(c) != 0) ctx->pair_xb = 0;
     CK(cudaMemcpyToSymbol(c_nes, nes4, sizeof(nes4)));
     CK(cudaFuncSetAttribute(k_blur_h, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlurHSmem));
     CK(cudaFuncSetAttribute(k_score_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V2Smem)));
@@ -528,6 +540,12 @@ extern "C" int snes_ctx_set_scorer(snes_ctx *ctx, int fused, int block_width, in
     return SNES_OK;
 }
 
+extern "C" int snes_ctx_set_all_terms(snes_ctx *ctx, int on) {
+    if (!ctx) return fail(SNES_E_INVALID, "ctx is NULL");
+    ctx->pair_xb = on ? 0 : weights_allow_pair_xb();
+    return SNES_OK;
+}
+
 extern "C" int snes_ctx_set_chunk(snes_ctx *ctx, int evaluations) {
     if (!ctx || evaluations < 1) return fail(SNES_E_INVALID, "snes_ctx_set_chunk: bad argument");
     ctx->chunk = evaluations;
@@ -654,16 +672,17 @@ static int launch_scorer(snes_ctx *ctx, const FusedArgs &fa, int ec, const Fused
     if (ctx->fused == 3) {
         V3Args va;
         va.f = fa;
-        va.nitems = 3 * ec;
+        va.nevals = ec;
         va.f2 = extra ? *extra : fa;
-        va.nitems2 = extra ? 3 * extra_evals : 0;
+        va.nevals2 = extra ? extra_evals : 0;
+        va.pair_xb = ctx->pair_xb;
         va.imgtm = ctx->d_imgtm;
         RET(tm_make_evals(&va.tm, fa.from_image ? nullptr : fa.maps, fa.xyb_rm, ec));
         if (extra) RET(tm_make_evals(&va.tm2, extra->from_image ? nullptr : extra->maps, extra->xyb_rm, extra_evals));
         else va.tm2 = va.tm;
         va.counter = ctx->v3_counter;
         va.hscratch = ctx->v3_scratch;
-        const int items = V3_PARTS * (va.nitems + va.nitems2);   // work items per (evaluation, channel): see k_score_v3
+        const int items = ((va.pair_xb ? 2 : 3) + (V3_PARTS - 1) * 3) * (va.nevals + va.nevals2);   // work items: see k_score_v3
         const int grid = items < ctx->nsm * V3_CTAS_PER_SM ? items : ctx->nsm * V3_CTAS_PER_SM;
         CK(cudaMemsetAsync(ctx->v3_counter, 0, sizeof(int), st));
         LAUNCH(ctx, "k_score_v3", k_score_v3<<<grid, V3_THREADS, sizeof(V3Smem), st>>>(va));
@@ -888,6 +907,7 @@ extern "C" int snes_image_new(snes_ctx *ctx, const uint8_t *rgba, int width, int
     };
     const size_t o_rgba = take(NPIX * 4), o_tp = take(NTILES), o_pal = take(MAX_ENTRIES * 3), o_map = take(NPIX);
     const size_t o_rm = take(plane), o_cm = take(plane), o_mu = take(plane), o_s11 = take(plane), o_ms = take(2 * plane);
+    const size_t o_bf = take(sizeof(float2) * NPIX);
     const size_t o_tab = take(sizeof(PalTables)), o_err = take(sizeof(double));
     const size_t o_lab = take(im->cfg.perceptual_palettes ? sizeof(float4) * NPIX : 0);
     const size_t o_alpha = take(NPIX);
@@ -907,6 +927,7 @@ extern "C" int snes_image_new(snes_ctx *ctx, const uint8_t *rgba, int width, int
     im->dev.mu1 = (float *)(b + o_mu);
     im->dev.s11 = (float *)(b + o_s11);
     im->dev.ms11 = (float2 *)(b + o_ms);
+    im->dev.bfxb = (float2 *)(b + o_bf);
     im->dev.tables = (PalTables *)(b + o_tab);
     im->dev.cur_err = (double *)(b + o_err);
     im->dev.lab = im->cfg.perceptual_palettes ? (const float *)(b + o_lab) : nullptr;
@@ -937,6 +958,7 @@ extern "C" int snes_image_new(snes_ctx *ctx, const uint8_t *rgba, int width, int
             LAUNCH(ctx, "k_blur_v", k_blur_v<<<(lines + 127) / 128, 128, 0, st>>>(s, lines, ctx->d_imgs, ctx->hbuf));
         }
         LAUNCH(ctx, "k_interleave_ms", k_interleave_ms<<<(EVAL_XYB_FLOATS + 255) / 256, 256, 0, st>>>(im->dev.mu1, im->dev.s11, im->dev.ms11, EVAL_XYB_FLOATS));
+        LAUNCH(ctx, "k_make_bfxb", k_make_bfxb<<<256, 256, 0, st>>>(im->dev));
         CK(cudaStreamSynchronize(st));
         return SNES_OK;
     };

@@ -86,6 +86,7 @@ _SIGNATURES = {
     "snes_ctx_set_stream": (_i, [_vp, _vp]),
     "snes_ctx_synchronize": (_i, [_vp]),
     "snes_ctx_set_chunk": (_i, [_vp, _i]),
+    "snes_ctx_set_all_terms": (_i, [_vp, _i]),
     "snes_ctx_set_transfer_luts": (_i, [_vp, _vp, _vp]),
     "snes_ctx_set_scorer": (_i, [_vp, _i, _i, _i]),
     "snes_ctx_profile_begin": (_i, [_vp]),
@@ -228,6 +229,10 @@ class Context:
         a = None if yuvxyb_eotf is None else np.ascontiguousarray(yuvxyb_eotf, np.float32).reshape(256)
         b = None if palette_eotf is None else np.ascontiguousarray(palette_eotf, np.float32).reshape(256)
         _check(self._l.snes_ctx_set_transfer_luts(self._h, _ptr(a), _ptr(b)), "snes_ctx_set_transfer_luts")
+
+    def set_all_terms(self, on: bool):
+        """on: the scorer computes ssim_map even where its pooling weights are zero (A/B check of the edge-only pair items)."""
+        _check(self._l.snes_ctx_set_all_terms(self._h, int(bool(on))), "snes_ctx_set_all_terms")
 
     def set_scorer(self, fused: int = 3, block_width: int = 32, delta_assign: bool = True):
         """fused: 3 = k_score_v3 (default), 2 = k_score_v2 (its predecessor, kept as the A/B check)."""

@@ -354,6 +354,29 @@ def test_scorer_variants_agree(ctx):
     assert np.max(np.abs(got["v3"] - got["v2"])) <= 1e-10
 
 
+def test_zero_weight_terms_are_skipped_without_changing_a_bit(ctx):
+    """ssim_map of (X, scale 0) and (B, scale 0) has pooling weight exactly 0.0 in SSIMULACRA2's table, so k_score_v3 computes only
+    edge_diff_map there (score_v3.cuh: v3_scale0_pair).  With every term switched back on, error() of the images and of their
+    candidates must be the same doubles -- with candidates, with the palette_map format of the images' own state, with
+    transparent pixels -- and equal the oracle's."""
+    rgba = synth.image(83, "T")
+    g, o = make_pair(ctx, rgba, 8, 15, seed=7)
+    for im in (g, o):
+        im.optimize()
+    cand = synth.candidates(83, 0, 12)
+    want = o.eval_candidates(2, 9, cand)
+    try:
+        ctx.set_all_terms(True)
+        full = (g.error(), g.eval_candidates(2, 9, cand), engine.batch_eval_candidates([g], 2, 9, cand[None])["scores"][0])
+        ctx.set_all_terms(False)
+        lean = (g.error(), g.eval_candidates(2, 9, cand), engine.batch_eval_candidates([g], 2, 9, cand[None])["scores"][0])
+    finally:
+        ctx.set_all_terms(False)
+    assert full[0] == lean[0] and np.array_equal(full[1], lean[1]) and np.array_equal(full[2], lean[2])
+    assert abs(lean[0] - o.error()) <= TIGHT_TOL and np.max(np.abs(lean[1] - want)) <= TIGHT_TOL
+    g.close()
+
+
 def test_sharded_argmin_matches_single_rank(ctx):
     """The candidate-sharded step of driver.BatchOptimizer, with the ranks emulated one after the other on one GPU:
     slice evaluation -> gathered (err, idx) records -> k_merge_best -> k_apply_best must equal the unsharded step."""
