@@ -10,6 +10,6 @@ timeout 120 python -c 'import __graft_entry__ as g; g.smoke()' > gpurun_out/${TA
 timeout 400 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
 cut -c1-600 gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-extras > gpurun_out/${TAG}_ncu1.log 2>&1; echo "ncu1 rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_score_v3 -s 8 -c 1 -f -o gpurun_out/${TAG}_prof python bench.py --steps 3 --warmup 3 --no-cpu --no-extras > gpurun_out/${TAG}_ncu2.log 2>&1; echo "ncu2 rc=$?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_score_ -s 16 -c 2 -f -o gpurun_out/${TAG}_prof python bench.py --steps 3 --warmup 3 --no-cpu --no-extras > gpurun_out/${TAG}_ncu2.log 2>&1; echo "ncu2 rc=$?"
 [ "$3" = "nostages" ] || bash scripts/stage_capture.sh
 du -sh gpurun_out

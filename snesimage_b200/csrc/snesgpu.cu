@@ -56,11 +56,13 @@ extern "C" int snes_version(void) { return 1; }
 struct snes_ctx {
     int device = 0;
     cudaStream_t own = nullptr, stream = nullptr;
+    cudaStream_t side = nullptr;              // k_score_v3 runs here next to k_score_pair on `stream` (fork / join by events)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int64_t launches = 0;
     int chunk = 2048;  // evaluations whose scratch (palette_map, coarse XYB pyramid) is live at once
     int fused = 3;    // 3: k_score_v3 (persistent 4-warp CTAs); 2: k_score_v2, its predecessor, kept as the A/B check (SNESGPU_FUSED)
     int nsm = 148;
-    int *v3_counter = nullptr;
+    int *v3_counter = nullptr;        // [2]: work counters of k_score_v3 and k_score_pair
     float *v3_scratch = nullptr;
     float *self_xyb = nullptr;        // [img_cap][EVAL_XYB_FLOATS] coarse pyramid of the images' own state (fused error + candidates)
     double *self_partials = nullptr;  // [img_cap][NSCALES*3*NSUMS]
@@ -188,6 +190,7 @@ static void prof_begin(snes_ctx *ctx, const char *name) {
     if (!ctx->profiling) return;
     ctx->prof_skip = !ctx->prof_filter.empty() && !strstr(name, ctx->prof_filter.c_str());
     if (ctx->prof_skip) return;
+    cudaStream_t st = ctx->stream;
     if (ctx->prof_used + 2 > ctx->prof_events.size()) {
         cudaEvent_t a, b;
         cudaEventCreate(&a);
@@ -196,7 +199,7 @@ static void prof_begin(snes_ctx *ctx, const char *name) {
         ctx->prof_events.push_back(b);
     }
     ctx->prof_names.push_back(name);
-    cudaEventRecord(ctx->prof_events[ctx->prof_used], ctx->stream);
+    cudaEventRecord(ctx->prof_events[ctx->prof_used], st);
 }
 static void prof_end(snes_ctx *ctx) {
     if (!ctx->profiling || ctx->prof_skip) return;
@@ -331,6 +334,9 @@ static int ctx_init(snes_ctx *ctx, int nsm) {
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&ctx->own, cudaStreamNonBlocking));
     ctx->stream = ctx->own;
+    CK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     if (const char *c = getenv("SNESGPU_CHUNK")) {
         const int v = atoi(c);
         if (v > 0) ctx->chunk = v;
@@ -386,11 +392,13 @@ static int ctx_init(snes_ctx *ctx, int nsm) {
     CK(cudaFuncSetAttribute(k_score_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V3Smem)));
     CK(cudaFuncSetAttribute(k_score_v3, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     ctx->nsm = nsm;
-    RET(dev_alloc(&ctx->v3_counter, 1));
+    RET(dev_alloc(&ctx->v3_counter, 2));
+    CK(cudaFuncSetAttribute(k_score_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V3PairSmem)));
+    CK(cudaFuncSetAttribute(k_score_pair, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     RET(dev_alloc(&ctx->hbuf, (size_t)EVAL_XYB_FLOATS * 2));
     RET(dev_alloc(&ctx->d_fault, 1));
     CK(cudaMemsetAsync(ctx->d_fault, 0, sizeof(int), ctx->stream));
-    RET(dev_alloc(&ctx->v3_scratch, (size_t)ctx->nsm * V3_CTAS_PER_SM * V3_HSCRATCH_FLOATS));
+    RET(dev_alloc(&ctx->v3_scratch, (size_t)ctx->nsm * (V3_CTAS_PER_SM + V3_PAIR_CTAS_PER_SM) * V3_HSCRATCH_FLOATS));
 
     RET(dev_alloc(&ctx->labtab, 32768));
     LAUNCH(ctx, "k_build_lab_table", k_build_lab_table<<<128, 256, 0, ctx->stream>>>(ctx->labtab));
@@ -431,6 +439,9 @@ extern "C" void snes_ctx_destroy(snes_ctx *ctx) {
     cudaFree(ctx->v3_counter);
     cudaFree(ctx->v3_scratch);
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->own) cudaStreamDestroy(ctx->own);
     delete ctx;
 }
@@ -682,10 +693,35 @@ static int launch_scorer(snes_ctx *ctx, const FusedArgs &fa, int ec, const Fused
         else va.tm2 = va.tm;
         va.counter = ctx->v3_counter;
         va.hscratch = ctx->v3_scratch;
-        const int items = ((va.pair_xb ? 2 : 3) + (V3_PARTS - 1) * 3) * (va.nevals + va.nevals2);   // work items: see k_score_v3
+        const int ne = va.nevals + va.nevals2;
+        const int items = ((va.pair_xb ? 1 : 3) + (V3_PARTS - 1) * 3) * ne;   // work items: see k_score_v3
         const int grid = items < ctx->nsm * V3_CTAS_PER_SM ? items : ctx->nsm * V3_CTAS_PER_SM;
-        CK(cudaMemsetAsync(ctx->v3_counter, 0, sizeof(int), st));
-        LAUNCH(ctx, "k_score_v3", k_score_v3<<<grid, V3_THREADS, sizeof(V3Smem), st>>>(va));
+        CK(cudaMemsetAsync(ctx->v3_counter, 0, 2 * sizeof(int), st));
+        if (va.pair_xb) {
+            // Scale 0 of channels X and B: one edge-only item per evaluation, in a kernel of its own (score_v3.cuh).  The two
+            // kernels are independent and run side by side: k_score_pair (few, long items) is launched first, k_score_v3 (its
+            // queue ends in many small items) on the side stream fills the SMs as the pair CTAs retire, so only one tail is
+            // exposed -- and for one picture, whose items do not fill the GPU, both grids are resident at once.
+            V3Args vp = va;
+            vp.counter = ctx->v3_counter + 1;
+            vp.hscratch = ctx->v3_scratch + (size_t)ctx->nsm * V3_CTAS_PER_SM * V3_HSCRATCH_FLOATS;
+            const int gp = ne < ctx->nsm * V3_PAIR_CTAS_PER_SM ? ne : ctx->nsm * V3_PAIR_CTAS_PER_SM;
+            // (profiling: one event pair on the launching stream around fork .. join -- the two kernels overlap, so their own
+            // brackets would count the overlap twice)
+            prof_begin(ctx, "k_score_pair+k_score_v3");
+            CK(cudaEventRecord(ctx->ev_fork, st));
+            CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+            k_score_pair<<<gp, V3_THREADS, sizeof(V3PairSmem), st>>>(vp);
+            CK(cudaGetLastError());
+            k_score_v3<<<grid, V3_THREADS, sizeof(V3Smem), ctx->side>>>(va);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(ctx->ev_join, ctx->side));
+            CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+            prof_end(ctx);
+            ctx->launches += 2;
+        } else {
+            LAUNCH(ctx, "k_score_v3", k_score_v3<<<grid, V3_THREADS, sizeof(V3Smem), st>>>(va));
+        }
     } else
         LAUNCH(ctx, "k_score_v2", k_score_v2<<<dim3(3, ec), V2_THREADS, sizeof(V2Smem), st>>>(fa));
     return SNES_OK;
