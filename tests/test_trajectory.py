@@ -3,8 +3,8 @@
   cfg1  8 x 15, RGB distance, no dither            cfg2  --perceptual-palettes (CIELAB), 4 x 7
   cfg3  --dither, 8 x 15                            cfg4  --nes --dither, 4 x 3
 
-k-means init + tile assignment, then ITERATIONS iterations of the schedule of run() (lib.rs:889-933), the state compared
-with the oracle's after EVERY iteration.  The oracle's 64 (56) candidate evaluations of an iteration are farmed over the
+k-means init + tile assignment, then 100 (cfg1: the whole of configs[0]) or 24 iterations of the schedule of run()
+(lib.rs:889-933), the state compared with the oracle's after EVERY iteration.  The oracle's 64 (56) candidate evaluations of an iteration are farmed over the
 host cores (one oracle image per worker process; `OraclePool`), so a config costs seconds instead of minutes.
 
 RGB metric (cfg1, cfg3, cfg4): palette, tile_palettes and palette_map bit-identical after every iteration; error within
@@ -22,7 +22,8 @@ from util import OraclePool, lab_choice_ok, oracle_entry_step
 
 pytestmark = pytest.mark.gpu
 
-ITERATIONS = 24
+ITERATIONS = 24              # cfg2..cfg4
+ITERATIONS_CFG1 = 100        # BASELINE.json configs[0] in full: k-means init + tile assignment + 100 optimiser iterations
 SCORE_TOL = 1e-4
 TIGHT_TOL = 1e-8
 LAB_TOL = 2e-4
@@ -52,8 +53,9 @@ def test_trajectory_rgb_metric_bit_exact(ctx, name):
     assert np.array_equal(r.image.palette, o.palette) and np.array_equal(r.image.palette_map, o.palette_map)
     cur = driver.Cursor()
     accepted = 0
+    iterations = ITERATIONS_CFG1 if name == "cfg1" else ITERATIONS
     with OraclePool(rgba, cfg) as pool:
-        for it in range(ITERATIONS):
+        for it in range(iterations):
             before = o.palette.copy()
             oracle_entry_step(o, pool, cur.mode(cfg), cur.palette, cur.palette_index, cur.channel, synth.candidates(0, it, 64))
             o.optimize()                                   # lib.rs:906-908
@@ -71,10 +73,10 @@ def test_trajectory_rgb_metric_bit_exact(ctx, name):
     # must land on the same trajectory -- state, cursor and the log of error changes
     r2 = driver.HeadlessRunner(ctx, rgba, cfg, seed=0, ncand=64, speculate=4)
     r2.initialize()
-    r2.iterate(ITERATIONS)
+    r2.iterate(iterations)
     assert np.array_equal(r2.image.palette, o.palette) and np.array_equal(r2.image.palette_map, o.palette_map), name
     assert r2.image.as_json() == o.as_json()
-    assert (r2.cursor.palette, r2.cursor.palette_index, r2.cursor.step, r2.iteration) == (cur.palette, cur.palette_index, cur.step, ITERATIONS)
+    assert (r2.cursor.palette, r2.cursor.palette_index, r2.cursor.step, r2.iteration) == (cur.palette, cur.palette_index, cur.step, iterations)
     assert r2.log == r.log and abs(r2.image.error() - o.error()) <= TIGHT_TOL
     r2.image.close()
     r.image.close()
