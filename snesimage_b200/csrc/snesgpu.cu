@@ -863,6 +863,7 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
     ctx->maps_ncand = pl.ncand;
     ctx->maps_slot = pl.ovr;
     ctx->maps_cand = pl.d_cand;
+    ctx->maps_images = ctx->cached;   // the images bind_images() bound for this plan
     if (pl.no_pool) return SNES_OK;
     if (pl.do_score && pl.d_best && !pl.self) {
         LAUNCH(ctx, "k_pool_argmin", k_pool_argmin<<<pl.nimg, 1024, 0, st>>>(ctx->d_imgs, self_too ? ctx->self_partials : nullptr, ctx->self_scores, ctx->partials,
@@ -1015,6 +1016,8 @@ extern "C" void snes_image_free(snes_image *im) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ctx->cached.clear();
+    ctx->maps_live = false;   // an image created later may reuse this address
+    ctx->maps_images.clear();
     cudaFree(im->slab);
     cudaFree(im->km_slab);
     delete im;
@@ -1317,7 +1320,6 @@ static int eval_candidates_dev(snes_ctx *ctx, snes_image *const *images, int nim
     pl.d_best = reinterpret_cast<Best *>(d_best);
     pl.best_idx_base = cand_idx_base;
     RET(run_plan(ctx, cfg, pl));
-    ctx->maps_images.assign(images, images + nimg);
     return SNES_OK;
 }
 
@@ -1543,7 +1545,6 @@ static int batch_step(snes_ctx *ctx, snes_image *const *images, int nimg, int pa
     pl.self_fresh = all_fresh(images, nimg);
     pl.d_best = ctx->best;
     RET(run_plan(ctx, cfg, pl));
-    ctx->maps_images.assign(images, images + nimg);
     RET(apply_and_optimize(ctx, images, nimg, slot, ctx->cand, ncand, ctx->best, mode == 1));
     if (best) CK(cudaMemcpyAsync(best, ctx->best, sizeof(Best) * nimg, cudaMemcpyDeviceToHost, st));
     if (errors_after) {
