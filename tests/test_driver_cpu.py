@@ -52,6 +52,19 @@ def test_cfg1_hundred_iterations_are_all_random():
     assert (cur.palette, cur.palette_index, cur.step) == (6, 10, 0)
 
 
+def test_lookahead_follows_the_accept_rate():
+    """HeadlessRunner.lookahead: one iteration per call while nearly every iteration accepts a candidate, deeper look-ahead as
+    accepts become rare, deeper still with dithering (a call's fixed cost is higher there), never beyond 4 x speculate, and 1 when
+    look-ahead is switched off.  Pure host logic: no GPU."""
+    class R(driver.HeadlessRunner):
+        def __init__(self, rate, dither=False, speculate=4):
+            self.speculate, self.accept_rate, self.config = speculate, rate, engine.Config(dither=dither)
+    ks = [R(a).lookahead() for a in (0.95, 0.5, 0.3, 0.1, 0.03, 0.01)]
+    assert ks[0] == 1 and ks == sorted(ks) and ks[-1] == 16
+    assert all(R(a, dither=True).lookahead() >= R(a).lookahead() for a in (0.9, 0.5, 0.2, 0.05))
+    assert R(0.01, speculate=1).lookahead() == 1 and R(0.01, speculate=2).lookahead() <= 8
+
+
 def test_shard_bounds_partition():
     for n in (1, 7, 56, 64, 4096):
         for world in (1, 2, 3, 4, 8):

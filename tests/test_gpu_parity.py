@@ -317,6 +317,28 @@ def test_batch_properties_full_size(ctx):
         im.close()
 
 
+def test_iterate_rejects_bad_arguments_and_reports_consumed_steps(ctx):
+    cfg = engine.Config(subpalette_count=2, subpalette_size=4)
+    g = engine.OptimizedImage(ctx, synth.image(9, "V"), cfg)
+    g.initialize_tiles()
+    g.recalculate_palettes()
+    pal = g.palette
+    with pytest.raises(engine.SnesGpuError):
+        g.iterate("random", [(2, 0)], synth.candidates(9, 0, 4)[None])            # subpalette out of range
+    with pytest.raises(engine.SnesGpuError):
+        g.iterate("channel", [(0, 1, 3)])                                         # channel out of range
+    with pytest.raises(engine.SnesGpuError):
+        g.iterate("random", [(0, 0)], np.full((1, 4, 3), 40, np.uint8))           # not a 5-bit colour
+    assert np.array_equal(g.palette, pal)
+    # candidates equal to the entries' own colours are never strictly better: every step is consumed, nothing changes, and
+    # the error before and after is error()
+    steps = [(0, 1), (1, 2), (1, 3)]
+    same = np.stack([np.repeat(pal[p * 4 + i][None], 5, axis=0) for p, i in steps])
+    used, before, after = g.iterate("random", steps, same)
+    assert used == 3 and before == after == g.error() and np.array_equal(g.palette, pal)
+    g.close()
+
+
 def test_invalid_arguments(ctx):
     cfg = engine.Config(subpalette_count=2, subpalette_size=4)
     with pytest.raises(engine.SnesGpuError):
