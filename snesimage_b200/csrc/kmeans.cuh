@@ -170,21 +170,32 @@ __device__ __forceinline__ void block_reduce_1024(double v[NV], double *s_red /*
 //   TILES == true : points = the image's tile means (f64, n = *nmeans), k = C, EXACT summation order;
 //                   afterwards tile_palettes[tile_map[i]] = assign[i]  (lib.rs:133-138).
 //   TILES == false: problem (image, subpalette p): points = pts[sub_off[p] .. sub_off[p+1]), k = S.
+//                   intpts != 0: the points are 8-bit integers (RGB mode).
 // Centres go to scr.centres[(TILES ? 0 : p*k) ..][3]; status[p] = -1 where cogset would panic.
 // grid = nimg * (TILES ? 1 : C), block 1024.
+//
+// Centre update in ONE pass over the points (round 2; it was k passes with a block reduction each):
+//   * integer points: a cluster's sums are sums of integers below 2^24, so any order gives the reference's value.  They are
+//     accumulated as u32 in shared memory while the assignment pass runs: the lanes of a warp that chose the same centre are
+//     found with match.any, their three components summed by redux.sync, and one lane adds the warp's share atomically.
+//   * tile means (f64, n <= 1024): the reference's sequential order matters, so cluster q's sum stays ONE thread's loop over the
+//     points in index order, as does the objective.  (Running the k chains on a second warp next to the objective chain, all from
+//     shared memory, was measured 2.3x SLOWER on B200 -- 1.68 against 0.73 ms for one picture, profiles/r2_kmeans_ab.txt -- and
+//     was dropped.)
+//   * Lab points (f64 sums of f32 values): still one fixed-order tree reduction per cluster; any order-free accumulation would
+//     make the sums run-to-run different.
 template <bool TILES>
-__global__ void __launch_bounds__(1024) k_kmeans(const ImgDev *imgs, const KmScratch *scr, int C, int k) {
+__global__ void __launch_bounds__(1024) k_kmeans(const ImgDev *imgs, const KmScratch *scr, int C, int k, int intpts) {
     __shared__ double s_cent[KM_MAXK][3];
-    __shared__ int s_cnt[KM_MAXK];
+    __shared__ unsigned s_acc[TILES ? 1 : KM_MAXK * 4];   // per cluster: sum r, sum g, sum b, count
     __shared__ double s_red[32 * 4];
     __shared__ double s_cost[TILES ? NTILES : 1];
     __shared__ int s_asg[TILES ? NTILES : 1];
     __shared__ double s_obj;
-    __shared__ int s_done;
     const int j = TILES ? blockIdx.x : blockIdx.x / C, p = TILES ? 0 : blockIdx.x % C;
     const ImgDev im = imgs[j];
     const KmScratch sc = scr[j];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int off = TILES ? 0 : sc.sub_off[p];
     const int n = TILES ? *sc.nmeans : sc.sub_off[p + 1] - off;
     const float *pts = sc.pts + 3 * (size_t)off;
@@ -211,27 +222,48 @@ __global__ void __launch_bounds__(1024) k_kmeans(const ImgDev *imgs, const KmScr
     double objective = 0.0;
     int iter = 0;
     for (int round = 0;; round++) {
-        // ---- update_assignments + objective ------------------------------------------------------
+        // ---- update_assignments + objective (+ the cluster sums of integer points) ----------------------
+        if (!TILES && intpts) {
+            for (int q = tid; q < 4 * k; q += 1024) s_acc[q] = 0u;
+            __syncthreads();
+        }
         double cost_sum = 0.0;
-        for (int i = tid; i < n; i += 1024) {
-            double a, b, c;
-            point(i, a, b, c);
-            int mi = 0;
-            double md = __longlong_as_double(0x7ff0000000000000ll);
-            for (int q = 0; q < k; q++) {
-                const double d0 = a - s_cent[q][0], d1 = b - s_cent[q][1], d2 = c - s_cent[q][2];
-                const double dd = (d0 * d0 + d1 * d1) + d2 * d2;
-                if (dd < md) {
-                    md = dd;
-                    mi = q;
+        for (int base = 0; base < n; base += 1024) {   // the same trip count for every lane of a warp
+            const int i = base + tid;
+            int mi = -1;
+            double a = 0.0, b = 0.0, c = 0.0;
+            if (i < n) {
+                point(i, a, b, c);
+                mi = 0;
+                double md = __longlong_as_double(0x7ff0000000000000ll);
+                for (int q = 0; q < k; q++) {
+                    const double d0 = a - s_cent[q][0], d1 = b - s_cent[q][1], d2 = c - s_cent[q][2];
+                    const double dd = (d0 * d0 + d1 * d1) + d2 * d2;
+                    if (dd < md) {
+                        md = dd;
+                        mi = q;
+                    }
+                }
+                if (TILES) {
+                    s_asg[i] = mi;
+                    s_cost[i] = md;
+                } else {
+                    if (!intpts) assign[i] = mi;
+                    cost_sum += md;
                 }
             }
-            if (TILES) {
-                s_asg[i] = mi;
-                s_cost[i] = md;
-            } else {
-                assign[i] = mi;
-                cost_sum += md;
+            if (!TILES && intpts) {
+                const unsigned peers = __match_any_sync(0xffffffffu, mi);
+                if (mi >= 0) {   // every lane of `peers` holds the same mi, so all of them are here
+                    const unsigned sr = __reduce_add_sync(peers, (unsigned)a), sg = __reduce_add_sync(peers, (unsigned)b),
+                                   sb = __reduce_add_sync(peers, (unsigned)c);
+                    if (lane == __ffs(peers) - 1) {
+                        atomicAdd(&s_acc[4 * mi], sr);
+                        atomicAdd(&s_acc[4 * mi + 1], sg);
+                        atomicAdd(&s_acc[4 * mi + 2], sb);
+                        atomicAdd(&s_acc[4 * mi + 3], (unsigned)__popc(peers));
+                    }
+                }
             }
         }
         double new_obj;
@@ -274,7 +306,13 @@ __global__ void __launch_bounds__(1024) k_kmeans(const ImgDev *imgs, const KmScr
                 s_cent[tid][0] = s0 * scale;
                 s_cent[tid][1] = s1 * scale;
                 s_cent[tid][2] = s2 * scale;
-                s_cnt[tid] = cnt;
+            }
+        } else if (intpts) {
+            if (tid < k) {
+                const double scale = 1.0 / (double)s_acc[4 * tid + 3];
+                s_cent[tid][0] = (double)s_acc[4 * tid] * scale;
+                s_cent[tid][1] = (double)s_acc[4 * tid + 1] * scale;
+                s_cent[tid][2] = (double)s_acc[4 * tid + 2] * scale;
             }
         } else {
             for (int q = 0; q < k; q++) {

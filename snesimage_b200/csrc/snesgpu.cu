@@ -813,9 +813,9 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
             if (pl.d_maps_out) {
                 uint8_t *outm = maps;
                 if (cfg.dither && cfg.perceptual_palettes)
-                    LAUNCH(ctx, "k_assign_dither<true>", k_assign_dither<true><<<ec, DITHER_THREADS, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, outm, 0, 0, pl.d_moves));
+                    LAUNCH(ctx, "k_assign_dither<true>", k_assign_dither<true><<<ec, DITHER_THREADS, dither_smem_bytes(CS, true), st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, outm, 0, 0, pl.d_moves));
                 else if (cfg.dither)
-                    LAUNCH(ctx, "k_assign_dither<false>", k_assign_dither<false><<<ec, DITHER_THREADS, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, outm, 0, 0, pl.d_moves));
+                    LAUNCH(ctx, "k_assign_dither<false>", k_assign_dither<false><<<ec, DITHER_THREADS, dither_smem_bytes(CS, false), st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, outm, 0, 0, pl.d_moves));
                 else if (cfg.perceptual_palettes)
                     LAUNCH(ctx, "k_assign_lab", k_assign_lab<<<dim3(64, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, outm, 0, 0, pl.d_moves));
                 else
@@ -825,9 +825,9 @@ static int run_plan(snes_ctx *ctx, const snes_config &cfg, const EvalPlan &pl) {
         }
         if (pl.do_assign) {
             if (cfg.dither && cfg.perceptual_palettes) {
-                LAUNCH(ctx, "k_assign_dither<true>", k_assign_dither<true><<<ec, DITHER_THREADS, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self, gi, pl.d_moves));
+                LAUNCH(ctx, "k_assign_dither<true>", k_assign_dither<true><<<ec, DITHER_THREADS, dither_smem_bytes(CS, true), st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self, gi, pl.d_moves));
             } else if (cfg.dither) {
-                LAUNCH(ctx, "k_assign_dither<false>", k_assign_dither<false><<<ec, DITHER_THREADS, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self, gi, pl.d_moves));
+                LAUNCH(ctx, "k_assign_dither<false>", k_assign_dither<false><<<ec, DITHER_THREADS, dither_smem_bytes(CS, false), st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self, gi, pl.d_moves));
             } else if (cfg.perceptual_palettes) {
                 LAUNCH(ctx, "k_assign_lab", k_assign_lab<<<dim3(64, ec), 256, 0, st>>>(ctx->d_imgs, ctx->cents, pl.ncand, e0, S, CS, pl.ovr, maps, pl.self, gi, pl.d_moves));
             } else {
@@ -1066,7 +1066,7 @@ static int batch_recalc(snes_ctx *ctx, snes_image *const *images, int nimg, int 
     LAUNCH(ctx, "k_gather_points", k_gather_points<<<nimg, 1024, 0, st>>>(ctx->d_imgs, ctx->d_km, cfg.subpalette_count, cfg.perceptual_palettes));
     for (int j = 0; j < nimg; j++) CK(cudaMemsetAsync(images[j]->km.status, 0xff, sizeof(int) * 2 * 256, st));
     // grid is (image, subpalette) with C as the stride; with only_sub0 the grid covers subpalette 0 only
-    LAUNCH(ctx, "k_kmeans<false>", k_kmeans<false><<<nimg * C, 1024, 0, st>>>(ctx->d_imgs, ctx->d_km, C, S));
+    LAUNCH(ctx, "k_kmeans<false>", k_kmeans<false><<<nimg * C, 1024, 0, st>>>(ctx->d_imgs, ctx->d_km, C, S, cfg.perceptual_palettes ? 0 : 1));
     LAUNCH(ctx, "k_centres_to_palette", k_centres_to_palette<<<nimg, 256, 0, st>>>(ctx->d_imgs, ctx->d_km, C, S, cfg.perceptual_palettes, cfg.nes, ctx->labtab, 0));
     std::vector<int> status((size_t)nimg * C);
     for (int j = 0; j < nimg; j++)
@@ -1096,7 +1096,7 @@ extern "C" int snes_batch_initialize_tiles(snes_ctx *ctx, snes_image *const *ima
     } else {
         LAUNCH(ctx, "k_tile_means", k_tile_means<<<nimg, 1024, 0, st>>>(ctx->d_imgs, ctx->d_km, cfg.perceptual_palettes));
         for (int j = 0; j < nimg; j++) CK(cudaMemsetAsync(images[j]->km.status, 0xff, sizeof(int) * 2 * 256, st));
-        LAUNCH(ctx, "k_kmeans<true>", k_kmeans<true><<<nimg, 1024, 0, st>>>(ctx->d_imgs, ctx->d_km, cfg.subpalette_count, cfg.subpalette_count));
+        LAUNCH(ctx, "k_kmeans<true>", k_kmeans<true><<<nimg, 1024, 0, st>>>(ctx->d_imgs, ctx->d_km, cfg.subpalette_count, cfg.subpalette_count, 0));
         LAUNCH(ctx, "k_centres_to_palette", k_centres_to_palette<<<nimg, 256, 0, st>>>(ctx->d_imgs, ctx->d_km, cfg.subpalette_count, cfg.subpalette_size,
                                                   cfg.perceptual_palettes, cfg.nes, ctx->labtab, 1));
         std::vector<int> status(nimg, -1);

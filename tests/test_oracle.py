@@ -120,9 +120,11 @@ def test_red_mean_formula_and_integer_key():
 
 
 def test_expanded_red_mean_key_and_rounding_rule_of_the_dither_kernel():
-    # snesimage_b200/csrc/dither.cuh evaluates the integer key with the target-only terms dropped,
+    # The expansion behind the dither kernel's packed key (snesimage_b200/csrc/dither_core.h; the packed form itself, with its
+    # per-pixel shift and the entry number in the low bits, is checked in tests/test_dither_core.py): the integer key with the
+    # target-only terms dropped,
     #   key'' = C0 + A r - R (r^2 + b^2) - 4096 G g + C1 b + 2B (r b)   (int32, wrap-around arithmetic)
-    # and must rank the entries of a pixel exactly like the full key (first strict minimum).  Exhaustive over the
+    # ranks the entries of a pixel exactly like the full key (first strict minimum).  Exhaustive over the
     # corners and a random sample of (target, entry) pairs, in int32 with overflow wrapping like the GPU.
     rng = np.random.RandomState(7)
     corners = np.array([[r, g, b] for r in (0, 1, 127, 128, 254, 255) for g in (0, 128, 255) for b in (0, 1, 128, 255)])
