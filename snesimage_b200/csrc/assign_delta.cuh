@@ -115,6 +115,8 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) k_assign_pyr(const Img
     __shared__ float s_lin[MAX_ENTRIES + 1][3];
     __shared__ float4 s_jobs[(MODE == 2) ? 1 : PYR_MAXJOBS];   // linear RGB + output offset of a queued pixel
     __shared__ int s_njobs;
+    __shared__ uint16_t s_queue[MODE == 1 ? 8 : 1][MODE == 1 ? 512 : 1];   // MODE 1: per warp, the pixels whose distance must be computed
+    __shared__ uint32_t s_take[MODE == 1 ? 8 : 1][32];                       // MODE 1: per warp and lane, the 16 decisions of the lane's block
     __shared__ float s2[3][32][33];   // linear RGB of the quadrant at scale 2
     __shared__ float s3[3][16][17];
     __shared__ float s4[3][8][9];
@@ -180,13 +182,23 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) k_assign_pyr(const Img
                 xkey = kk.y;
             }
         };
-        // MODE 1: CIEDE2000 is expensive and only ~1/C of the blocks are affected, so the warp pools them: two affected
-        // blocks at a time, one pixel per lane, and the 16 decisions of a block return to its owner through a ballot
+        // MODE 1: CIEDE2000 is expensive and only ~1/C of the blocks are affected, so the warp pools them.  Two passes:
+        //   A  two affected blocks at a time, one pixel per lane: a lower bound of the candidate's distance from the lightness
+        //      term alone decides most pixels without the formula (below); the pixels it cannot decide are queued per warp;
+        //   B  the queue, 32 pixels at a time: the full distance; a "take" sets the pixel's bit in its owner's word.
+        // Lower bound: dE00^2 = a^2 + b^2 + c^2 + RT b c with a = dL'/SL, b = dC'/SC, c = dH'/SH and |RT| <= 2 sqrt(x / (x + 25^7)) < 2,
+        // so b^2 + c^2 + RT b c >= (1 - |RT|/2)(b^2 + c^2) >= 0 and dE00 >= |dL|/SL; SL = 1 + 0.015 m / sqrt(20 + m), m = (Lbar - 50)^2
+        // <= 2500, is at most 1.747.  A candidate whose |dL| / 1.75 exceeds the pixel's threshold (the key of the best of the other
+        // entries) by more than the margin below cannot win or tie, whatever the f32 evaluation of the formula rounds to.
         uint32_t takebits = 0;
         if (MODE == 1) {
-            const int lane = tid & 31;
+            const int lane = tid & 31, wp = tid >> 5;
+            uint16_t *queue = s_queue[wp];
+            s_take[wp][lane] = 0u;
+            __syncwarp();
             const bool aff = (a4[0] | a4[1] | a4[2] | a4[3]) != 0u;
             unsigned mask = __ballot_sync(0xffffffffu, aff);
+            int nq = 0;
             while (mask) {
                 const int sa = __ffs(mask) - 1;
                 mask &= mask - 1;
@@ -200,20 +212,35 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) k_assign_pyr(const Img
                 const uint32_t w2 = __shfl_sync(0xffffffffu, g4[2], src), w3 = __shfl_sync(0xffffffffu, g4[3], src);
                 const uint32_t w = r == 0 ? w0 : (r == 1 ? w1 : (r == 2 ? w2 : w3));
                 const int gi = (w >> (8 * c)) & 255;
-                bool take = false;
+                bool undecided = false;
+                const int px = (sy0 + r) * W + sx0 + c;
                 if (gi >= psub && gi < psub + S && (lane < 16 || hasb)) {
-                    const int px = (sy0 + r) * W + sx0 + c;
-                    const float4 t = __ldg(reinterpret_cast<const float4 *>(im.lab) + px);
-                    const float d = ciede2000(ce.lab[0], ce.lab[1], ce.lab[2], t.x, t.y, t.z);
                     int xi, xkey;
                     others(px, gi - psub, xi, xkey);
                     const float xb = __int_as_float(xkey);
-                    take = d < xb || (d == xb && oloc < xi);
+                    const float tl = __ldg(im.lab + 4 * (size_t)px);   // L of the pixel
+                    const float lb = fabsf(ce.lab[0] - tl) * (1.0f / 1.75f);
+                    undecided = !(lb > __fmaf_rn(xb, 1.001f, 1e-3f));   // (NaN or infinite thresholds stay undecided)
                 }
-                const unsigned tb = __ballot_sync(0xffffffffu, take);
-                if (lane == sa) takebits = tb & 0xffffu;
-                if (hasb && lane == sb) takebits = tb >> 16;
+                const unsigned ub = __ballot_sync(0xffffffffu, undecided);
+                if (undecided) queue[nq + __popc(ub & ((1u << lane) - 1u))] = (uint16_t)px;
+                nq += __popc(ub);
             }
+            __syncwarp();
+            for (int sidx = lane; sidx < nq; sidx += 32) {
+                const int px = queue[sidx], py = px >> 8, pxx = px & 255;
+                const int gi = im.base_gi[px];
+                const float4 t = __ldg(reinterpret_cast<const float4 *>(im.lab) + px);
+                const float d = ciede2000(ce.lab[0], ce.lab[1], ce.lab[2], t.x, t.y, t.z);
+                int xi, xkey;
+                others(px, gi - psub, xi, xkey);
+                const float xb = __int_as_float(xkey);
+                if (d < xb || (d == xb && oloc < xi))
+                    atomicOr(&s_take[wp][(pxx >> 2) & 31], 1u << (4 * (py & 3) + (pxx & 3)));   // owner lane = the block's column
+            }
+            __syncwarp();
+            takebits = s_take[wp][lane];
+            __syncwarp();
         }
         float l1[2][2][3];
         float quad[4][4][3];
