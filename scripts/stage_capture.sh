@@ -10,6 +10,6 @@ for mode in ${STAGE_MODES:-rgb lab dither}; do
 done
 ls -la gpurun_out/s_*
 # the dither kernel once more at 16 images x 64 candidates (1024 CTAs: ~7 of its 8 CTAs per SM resident), its working occupancy
-timeout 300 ncu --set full --clock-control none --kernel-name-base demangled -k regex:k_assign_dither -s 1 -c 1 -f -o /tmp/s_dither16 python scripts/quick_bench.py 16 dither v3 > gpurun_out/s_ncu_dither16.log 2>&1
+timeout 300 ncu --set full --clock-control none --kernel-name-base demangled -k regex:k_assign_dither -s 1 -c 4 -f -o /tmp/s_dither16 python scripts/quick_bench.py 16 dither v3 > gpurun_out/s_ncu_dither16.log 2>&1
 echo "dither16 rc=$?"
 ncu -i /tmp/s_dither16.ncu-rep --page raw --csv > gpurun_out/s_dither16_raw.csv 2>/dev/null
