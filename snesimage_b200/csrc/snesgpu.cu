@@ -557,6 +557,33 @@ extern "C" int snes_ctx_set_all_terms(snes_ctx *ctx, int on) {
     return SNES_OK;
 }
 
+// every float with bit pattern in [lo_bits, hi_bits): msun_cbrtf against msun_cbrtf_fast
+__global__ void k_cbrt_selfcheck(uint32_t lo_bits, uint32_t hi_bits, unsigned long long *mismatches, unsigned *fallbacks) {
+    unsigned long long bad = 0;
+    for (unsigned long long b = lo_bits + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < hi_bits; b += (unsigned long long)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((uint32_t)b);
+        bad += __float_as_uint(msun_cbrtf(x)) != __float_as_uint(msun_cbrtf_fast(x, fallbacks));
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+extern "C" int snes_ctx_cbrt_selfcheck(snes_ctx *ctx, uint32_t lo_bits, uint32_t hi_bits, uint64_t *mismatches, uint64_t *fallbacks) {
+    if (!ctx || !mismatches || !fallbacks || hi_bits < lo_bits) return fail(SNES_E_INVALID, "snes_ctx_cbrt_selfcheck: bad argument");
+    unsigned long long *d = nullptr;
+    CK(cudaMalloc(&d, 16));
+    CK(cudaMemsetAsync(d, 0, 16, ctx->stream));
+    k_cbrt_selfcheck<<<148 * 8, 256, 0, ctx->stream>>>(lo_bits, hi_bits, d, reinterpret_cast<unsigned *>(d + 1));
+    unsigned long long h[2] = {0, 0};
+    const cudaError_t e = cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, ctx->stream);
+    const cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    CK(e);
+    CK(e2);
+    *mismatches = h[0];
+    *fallbacks = h[1] & 0xffffffffull;
+    return SNES_OK;
+}
+
 extern "C" int snes_ctx_set_chunk(snes_ctx *ctx, int evaluations) {
     if (!ctx || evaluations < 1) return fail(SNES_E_INVALID, "snes_ctx_set_chunk: bad argument");
     ctx->chunk = evaluations;

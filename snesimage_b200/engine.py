@@ -87,6 +87,7 @@ _SIGNATURES = {
     "snes_ctx_synchronize": (_i, [_vp]),
     "snes_ctx_set_chunk": (_i, [_vp, _i]),
     "snes_ctx_set_all_terms": (_i, [_vp, _i]),
+    "snes_ctx_cbrt_selfcheck": (_i, [_vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "snes_ctx_set_transfer_luts": (_i, [_vp, _vp, _vp]),
     "snes_ctx_set_scorer": (_i, [_vp, _i, _i, _i]),
     "snes_ctx_profile_begin": (_i, [_vp]),
@@ -233,6 +234,13 @@ class Context:
     def set_all_terms(self, on: bool):
         """on: the scorer computes ssim_map even where its pooling weights are zero (A/B check of the edge-only pair items)."""
         _check(self._l.snes_ctx_set_all_terms(self._h, int(bool(on))), "snes_ctx_set_all_terms")
+
+    def cbrt_selfcheck(self, lo: float, hi: float):
+        """Compare the kernels' cube root with the restated msun cbrtf on every float in [lo, hi): (mismatches, fallbacks)."""
+        lo_bits, hi_bits = (int(np.float32(v).view(np.uint32)) for v in (lo, hi))
+        bad, fb = C.c_uint64(0), C.c_uint64(0)
+        _check(self._l.snes_ctx_cbrt_selfcheck(self._h, lo_bits, hi_bits, C.byref(bad), C.byref(fb)), "snes_ctx_cbrt_selfcheck")
+        return bad.value, fb.value
 
     def set_scorer(self, fused: int = 3, block_width: int = 32, delta_assign: bool = True):
         """fused: 3 = k_score_v3 (default), 2 = k_score_v2 (its predecessor, kept as the A/B check)."""

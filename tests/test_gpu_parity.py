@@ -17,6 +17,17 @@ TIGHT_TOL = 1e-8
 LAB_TOL = 2e-4     # excess CIEDE2000 distance allowed for a differing CIELAB choice
 
 
+def test_fast_cbrt_is_the_exact_one(ctx):
+    """The kernels' cube root (one f32 + one division-free f64 Halley step, exact fallback near f32 rounding boundaries) against the
+    restated msun cbrtf, on EVERY float of the range the opsin transfer can produce and well beyond: [2^-9, 2) = 83,886,080 inputs
+    (the mixed linear values lie in [0.0037, 1.004]), plus the subnormal / zero end, which goes to the exact path."""
+    bad, fb = ctx.cbrt_selfcheck(2.0 ** -9, 2.0)
+    assert bad == 0
+    assert 0 < fb < 84e6 * 2e-4            # the fallback exists and is rare (6e-5 expected)
+    bad, fb = ctx.cbrt_selfcheck(0.0, 2.0 ** -120)
+    assert bad == 0
+
+
 @pytest.mark.parametrize("family", ["V", "G", "B", "T"])
 def test_source_planes_bit_exact(ctx, family):
     rgba = synth.image(3, family)
