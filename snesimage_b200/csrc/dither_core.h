@@ -101,6 +101,7 @@ DC_HD int nearest_rgb(const KeyCoef *tab, int S, int r, int g, int b) {
         const bool hi = (m1 >> 3) < (m0 >> 3);   // equal keys: the lower group wins
         return hi ? 8 + (m1 & 7) : (m0 & 7);
     }
+    if (S == 3) return imin(imin(DC_V(0), DC_V(1)), DC_V(2)) & 7;   // the NES configuration (4 x 3 colours)
     int bestk = 0x7fffffff, bi = 0;
     for (int j0 = 0; j0 < S; j0 += 8) {
         int m = DC_V(j0);
