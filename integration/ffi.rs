@@ -55,4 +55,7 @@ unsafe extern "C" {
                               ncand: c_int, consumed: *mut c_int, error_before: *mut f64, error_after: *mut f64) -> c_int;
     // verified 256-entry sRGB -> linear tables (yuvxyb's, palette's) in place of the built-in ones; before any image exists
     pub fn snes_ctx_set_transfer_luts(ctx: *mut SnesCtx, yuvxyb_eotf: *const f32, palette_eotf: *const f32) -> c_int;
+    // diagnostics: the kernels' cube root against the restated yuvxyb-math cbrtf on every f32 bit pattern in [lo_bits, hi_bits);
+    // `mismatches` must come back 0 (a maintainer with the crate can also feed the same range through yuvxyb_math::cbrtf)
+    pub fn snes_ctx_cbrt_selfcheck(ctx: *mut SnesCtx, lo_bits: u32, hi_bits: u32, mismatches: *mut u64, fallbacks: *mut u64) -> c_int;
 }

@@ -83,7 +83,9 @@ def test_eval_candidates_rgb(ctx, family, C, S, dither):
     assert r["best"]["idx"][0] == k and abs(r["best"]["err"][0] - so[k]) <= TIGHT_TOL
 
 
-@pytest.mark.parametrize("family,C,S", [("V", 8, 15), ("G", 2, 7), ("T", 4, 3), ("B", 1, 2)])
+# (16 x 16 = the largest palette the tables hold, S = 16 two full groups of packed keys, S = 9 one full + one partial group,
+# S = 1 a single entry; 8 x 15 and 4 x 3 take the straight-line searches)
+@pytest.mark.parametrize("family,C,S", [("V", 8, 15), ("G", 2, 7), ("T", 4, 3), ("B", 1, 2), ("T", 16, 16), ("V", 5, 9), ("G", 3, 1)])
 def test_dither_rgb_bit_exact(ctx, family, C, S):
     rgba = synth.image(31, family)
     g, o = make_pair(ctx, rgba, C, S, dither=True, seed=9)
