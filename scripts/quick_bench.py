@@ -27,6 +27,14 @@ for name in modes:
         ctx.set_chunk(chunk)
         engine.batch_eval_candidates(imgs, 0, 0, cand, want_scores=False)
         reps = 3
+        if "noprof" in sys.argv[4:]:   # wall time only: with every kernel timed on its own the library does not overlap launches
+            reps = 10
+            t = time.time()
+            for _ in range(reps):
+                engine.batch_eval_candidates(imgs, 0, 0, cand, want_scores=False)
+            dt = (time.time() - t) / reps
+            print(f"[{name}] {label:13s}: wall {dt * 1e3:7.3f} ms/step unprofiled  {nimg * ncand / dt:9.0f} evals/s", flush=True)
+            continue
         ctx.profile_begin()
         t = time.time()
         for _ in range(reps):
