@@ -127,36 +127,47 @@ __device__ __forceinline__ float msun_cbrtf(float x) {
 // range).  (float)t2' can differ from (float)t2 only if a rounding boundary of f32 -- a midpoint between two floats -- lies between
 // them, so whenever t2' is within 2^-39 of a midpoint (bits 28..0 of its mantissa within 2^14 of 0x10000000: 6 inputs in 100,000)
 // the exact function is evaluated instead.  What it saves is the FP64 pipe: two f64 divisions and ~60 FP64 instructions per cube
-// root become ~10 (k_assign_pyr<2> converts 84 M pixels per 4096 dithered evaluations).
+// root become ~10 (k_assign_pyr<2> converts 84 M pixels per 4096 dithered evaluations), and its five f32 <-> f64 conversions leave
+// the XU pipe (integer widening / narrowing of positive normal numbers), which the reciprocals need.
 #ifndef SNES_EXACT_CBRT
 #define SNES_EXACT_CBRT 0   // 1: every cube root through msun_cbrtf (A/B runs)
 #endif
 // (the rare path as a real call: three inlined copies of the exact function per pixel conversion cost more in code size and
 // registers than the fast path saves in CIELAB mode)
 __device__ __noinline__ float msun_cbrtf_call(float x) { return msun_cbrtf(x); }
+// f32 <-> f64 of positive normal numbers by integer operations (exact widening; narrowing toward zero): the conversion
+// instructions share the quarter-rate XU pipe with the two reciprocals below, which is what bounds the conversion kernels
+__device__ __forceinline__ double widen_pos(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
+}
+__device__ __forceinline__ uint32_t narrow_pos_bits(double d) {
+    return (((uint32_t)__double2hiint(d) - 0x38000000u) << 3) | ((uint32_t)__double2loint(d) >> 29);
+}
 __device__ __forceinline__ float msun_cbrtf_fast(float x, unsigned *fallbacks = nullptr) {
 #if SNES_EXACT_CBRT
     return msun_cbrtf(x);
 #else
-    const uint32_t bits = __float_as_uint(x), hx = bits & 0x7fffffffu, sign = bits & 0x80000000u;
-    if (hx - 0x00800000u >= 0x7f000000u) return msun_cbrtf_call(x);   // zero, subnormal, infinite, NaN
-    const float t0 = __uint_as_float(sign | (hx / 3 + 709958130u));
+    const uint32_t bits = __float_as_uint(x);
+    if (bits - 0x00800000u >= 0x7f000000u) return msun_cbrtf_call(x);   // zero, subnormal, infinite, NaN, negative
+    const float t0 = __uint_as_float(bits / 3 + 709958130u);
     const float r0 = (t0 * t0) * t0;
     const float t1 = t0 * __fdividef((x + x) + r0, (x + r0) + r0);
-    const double t = (double)t1, xd = (double)x;
+    const double t = widen_pos(t1), xd = widen_pos(x);
     const double r = t * t * t;
     const double num = xd + xd + r, den = xd + r + r;
     float rf;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)den));
-    double rd = (double)rf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(__uint_as_float(narrow_pos_bits(den))));
+    double rd = widen_pos(rf);
     rd = fma(rd, fma(-den, rd, 1.0), rd);
     const double t2 = (t * num) * rd;
-    const int low29 = __double2loint(t2) & 0x1fffffff;
-    if (abs(low29 - (1 << 28)) < (1 << 14)) {
+    const uint32_t lo = (uint32_t)__double2loint(t2);
+    if (abs((int)(lo & 0x1fffffffu) - (1 << 28)) < (1 << 14)) {
         if (fallbacks) atomicAdd(fallbacks, 1u);
         return msun_cbrtf_call(x);
     }
-    return (float)t2;
+    // (float)t2, round to nearest: t2 is not within 2^14 units of a tie, so adding the first dropped bit is the whole rule
+    return __uint_as_float(narrow_pos_bits(t2) + ((lo >> 28) & 1u));
 #endif
 }
 
