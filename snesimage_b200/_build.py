@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libsnesgpu.so")
 SOURCES = ["snesgpu.cu"]
-HEADERS = ["common.cuh", "kernels.cuh", "lab.cuh", "dither.cuh", "kmeans.cuh", "score_common.cuh", "score_v2.cuh", "score_v3.cuh", "assign_delta.cuh", os.path.join("..", "..", "include", "snesgpu.h")]
+HEADERS = ["common.cuh", "kernels.cuh", "lab.cuh", "dither.cuh", "dither_core.h", "kmeans.cuh", "score_common.cuh", "score_v2.cuh", "score_v3.cuh", "assign_delta.cuh", os.path.join("..", "..", "include", "snesgpu.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
