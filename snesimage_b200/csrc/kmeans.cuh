@@ -14,6 +14,8 @@
 // reference's loop.  Only the objective of the per-pixel problems and the Lab cluster sums can differ
 // from a sequential sum, by rounding in the last bits.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "lab.cuh"
 
@@ -348,6 +350,126 @@ __global__ void __launch_bounds__(1024) k_kmeans(const ImgDev *imgs, const KmScr
     if (tid == 0) {
         sc.status[p] = 0;
         sc.status[C + p] = iter;
+    }
+}
+
+// k_kmeans<false> for integer points when there are few problems (one picture: C problems on 148 SMs): the points of a problem are
+// spread over a thread-block cluster of KM_CLUSTER CTAs.  Every CTA assigns its share and accumulates its own integer sums and its
+// share of the objective; after one cluster barrier every CTA reads all partial results through distributed shared memory in rank
+// order -- the same totals and the same objective in every CTA, so all of them take the same decision and compute the same centres
+// (redundantly) for the next pass.  The accumulators are double-buffered, which makes that barrier the only one of an iteration.
+// Integer sums are exact in any order, so the centres are those of the one-CTA kernel; the objective is the sum of the CTAs'
+// fixed-order partial sums (it only decides when to stop: |change| < 1e-6).
+// grid = problems x KM_CLUSTER, block 1024.
+constexpr int KM_CLUSTER = 8;
+__global__ void __cluster_dims__(KM_CLUSTER, 1, 1) __launch_bounds__(1024) k_kmeans_cluster(const ImgDev *imgs, const KmScratch *scr, int C, int k) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    __shared__ double s_cent[KM_MAXK][3];
+    __shared__ unsigned s_acc[2][KM_MAXK * 4];   // [buffer][cluster: sum r, sum g, sum b, count] of THIS CTA's points
+    __shared__ double s_costpart[2];
+    __shared__ unsigned s_tot[KM_MAXK * 4];
+    __shared__ double s_red[32 * 4];
+    __shared__ double s_obj;
+    const int prob = blockIdx.x / KM_CLUSTER, j = prob / C, p = prob % C;
+    const KmScratch sc = scr[j];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int off = sc.sub_off[p];
+    const int n = sc.sub_off[p + 1] - off;
+    const float *pts = sc.pts + 3 * (size_t)off;
+    double *centres = sc.centres + 3 * (size_t)(p * k);
+    if (!(2 <= k && k < n)) {  // cogset: assert!(2 <= k && k < data.len())   (the same in every CTA of the cluster)
+        if (rank == 0 && tid == 0) sc.status[p] = -1;
+        return;
+    }
+    if (tid < k) {
+        s_cent[tid][0] = (double)pts[3 * tid];
+        s_cent[tid][1] = (double)pts[3 * tid + 1];
+        s_cent[tid][2] = (double)pts[3 * tid + 2];
+    }
+    __syncthreads();
+    double objective = 0.0;
+    int iter = 0, buf = 0;
+    for (int round = 0;; round++, buf ^= 1) {
+        for (int q = tid; q < 4 * k; q += 1024) s_acc[buf][q] = 0u;
+        __syncthreads();
+        double cost_sum = 0.0;
+        for (int base = 0; base < n; base += 1024 * KM_CLUSTER) {
+            const int i = base + rank * 1024 + tid;
+            int mi = -1;
+            double a = 0.0, b = 0.0, c = 0.0;
+            if (i < n) {
+                a = (double)pts[3 * i];
+                b = (double)pts[3 * i + 1];
+                c = (double)pts[3 * i + 2];
+                mi = 0;
+                double md = __longlong_as_double(0x7ff0000000000000ll);
+                for (int q = 0; q < k; q++) {
+                    const double d0 = a - s_cent[q][0], d1 = b - s_cent[q][1], d2 = c - s_cent[q][2];
+                    const double dd = (d0 * d0 + d1 * d1) + d2 * d2;
+                    if (dd < md) {
+                        md = dd;
+                        mi = q;
+                    }
+                }
+                cost_sum += md;
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, mi);
+            if (mi >= 0) {
+                const unsigned sr = __reduce_add_sync(peers, (unsigned)a), sg = __reduce_add_sync(peers, (unsigned)b),
+                               sb = __reduce_add_sync(peers, (unsigned)c);
+                if (lane == __ffs(peers) - 1) {
+                    atomicAdd(&s_acc[buf][4 * mi], sr);
+                    atomicAdd(&s_acc[buf][4 * mi + 1], sg);
+                    atomicAdd(&s_acc[buf][4 * mi + 2], sb);
+                    atomicAdd(&s_acc[buf][4 * mi + 3], (unsigned)__popc(peers));
+                }
+            }
+        }
+        double v[1] = {cost_sum};
+        block_reduce_1024<1>(v, s_red);
+        if (tid == 0) s_costpart[buf] = v[0];
+        cluster.sync();   // every CTA's partial results of this pass are complete and visible
+        if (tid < 4 * k) {
+            unsigned t = 0;
+            for (int r = 0; r < KM_CLUSTER; r++) t += cluster.map_shared_rank(&s_acc[buf][0], r)[tid];
+            s_tot[tid] = t;
+        }
+        if (tid == 0) {
+            double o = 0.0;
+            for (int r = 0; r < KM_CLUSTER; r++) o += *cluster.map_shared_rank(&s_costpart[buf], r);
+            s_obj = o;
+        }
+        __syncthreads();
+        const double new_obj = s_obj;
+        if (round > 0) {
+            if (fabs(new_obj - objective) < KM_TOL) break;
+            objective = new_obj;
+            iter++;
+            if (iter >= KM_MAX_ITER) break;
+        } else {
+            objective = new_obj;
+        }
+        if (tid < k) {
+            const double scale = 1.0 / (double)s_tot[4 * tid + 3];
+            s_cent[tid][0] = (double)s_tot[4 * tid] * scale;
+            s_cent[tid][1] = (double)s_tot[4 * tid + 1] * scale;
+            s_cent[tid][2] = (double)s_tot[4 * tid + 2] * scale;
+        }
+        __syncthreads();
+    }
+    cluster.sync();   // no CTA leaves while its shared memory may still be read
+    if (rank == 0) {
+        if (tid < k) {
+            centres[3 * tid] = s_cent[tid][0];
+            centres[3 * tid + 1] = s_cent[tid][1];
+            centres[3 * tid + 2] = s_cent[tid][2];
+        }
+        if (tid == 0) {
+            sc.status[p] = 0;
+            sc.status[C + p] = iter;
+        }
     }
 }
 

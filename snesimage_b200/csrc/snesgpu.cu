@@ -66,6 +66,7 @@ struct snes_ctx {
     float *v3_scratch = nullptr;
     float *self_xyb = nullptr;        // [img_cap][EVAL_XYB_FLOATS] coarse pyramid of the images' own state (fused error + candidates)
     double *self_partials = nullptr;  // [img_cap][NSCALES*3*NSUMS]
+    bool no_cluster_kmeans = false;   // env SNESGPU_NO_CLUSTER_KMEANS=1: one CTA per k-means problem whatever their number (A/B runs)
     int pair_xb = 0;  // scale 0 of channels X and B carries no ssim_map weight in the pooling table: edge-only pair items (score_v3.cuh)
     int delta = 1;    // 1: no-dither candidates re-decide only the pixels the replaced entry can change (SNESGPU_DELTA)
 
@@ -344,6 +345,7 @@ static int ctx_init(snes_ctx *ctx, int nsm) {
 
     if (const char *c = getenv("SNESGPU_FUSED")) ctx->fused = atoi(c) == 2 ? 2 : 3;
     if (const char *c = getenv("SNESGPU_DELTA")) ctx->delta = atoi(c) != 0;
+    if (const char *c = getenv("SNESGPU_NO_CLUSTER_KMEANS")) ctx->no_cluster_kmeans = atoi(c) != 0;
 
     float lut[256], lut2[256], n2[3], d1[3];
     for (int v = 0; v < 256; v++) {
@@ -1093,7 +1095,11 @@ static int batch_recalc(snes_ctx *ctx, snes_image *const *images, int nimg, int 
     LAUNCH(ctx, "k_gather_points", k_gather_points<<<nimg, 1024, 0, st>>>(ctx->d_imgs, ctx->d_km, cfg.subpalette_count, cfg.perceptual_palettes));
     for (int j = 0; j < nimg; j++) CK(cudaMemsetAsync(images[j]->km.status, 0xff, sizeof(int) * 2 * 256, st));
     // grid is (image, subpalette) with C as the stride; with only_sub0 the grid covers subpalette 0 only
-    LAUNCH(ctx, "k_kmeans<false>", k_kmeans<false><<<nimg * C, 1024, 0, st>>>(ctx->d_imgs, ctx->d_km, C, S, cfg.perceptual_palettes ? 0 : 1));
+    // few integer problems (one picture): a thread-block cluster of KM_CLUSTER CTAs per problem (kmeans.cuh); otherwise one CTA each
+    if (!cfg.perceptual_palettes && nimg * C * KM_CLUSTER <= 2 * ctx->nsm && !ctx->no_cluster_kmeans)
+        LAUNCH(ctx, "k_kmeans_cluster", k_kmeans_cluster<<<nimg * C * KM_CLUSTER, 1024, 0, st>>>(ctx->d_imgs, ctx->d_km, C, S));
+    else
+        LAUNCH(ctx, "k_kmeans<false>", k_kmeans<false><<<nimg * C, 1024, 0, st>>>(ctx->d_imgs, ctx->d_km, C, S, cfg.perceptual_palettes ? 0 : 1));
     LAUNCH(ctx, "k_centres_to_palette", k_centres_to_palette<<<nimg, 256, 0, st>>>(ctx->d_imgs, ctx->d_km, C, S, cfg.perceptual_palettes, cfg.nes, ctx->labtab, 0));
     std::vector<int> status((size_t)nimg * C);
     for (int j = 0; j < nimg; j++)
