@@ -11,7 +11,7 @@
 //
 // The step itself is dc::step (dither_core.h, also compiled for the host by tests/test_dither_core.py).  What this
 // generation changes against round 2's first kernel (4.61 -> 3.64 ms per 4096 evaluations, profiles/r2_dither_ab.txt) is the instruction count
-// of a step -- the kernel runs at IPC 2.3 with six CTAs per SM, so instructions are what it pays for:
+// of a step -- the kernel runs at IPC 2.2-2.4 with eight CTAs per SM, so instructions are what it pays for:
 //   * the loop is unrolled by three and the window's roles rotate with the step number: no register moves;
 //     the mailbox is a ring of three buffers addressed by the same step number: no pointer swaps;
 //   * packed keys (dither_core.h): v = 8 key' + entry number as one int32, minimum by VIMNMX -- 8 instead of 10 instructions
