@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) k_assign_pyr(const Img
             __syncwarp();
         }
         float l1[2][2][3];
-        float quad[4][4][3];
+        uint32_t outw[4];
         bool changed = false;
 #pragma unroll
         for (int r = 0; r < 4; r++) {
@@ -275,26 +275,38 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) k_assign_pyr(const Img
                 const uint32_t v = out4 ^ ovr_rep;
                 changed |= out4 != g4[r] || ((v - 0x01010101u) & ~v & 0x80808080u) != 0;
             }
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const int gi = (out4 >> (8 * c)) & 255;
-                quad[r][c][0] = s_lin[gi][0];
-                quad[r][c][1] = s_lin[gi][1];
-                quad[r][c][2] = s_lin[gi][2];
-            }
+            outw[r] = out4;
         }
-        // downscale_by_2: ((p00 + p01) + p10) + p11, * 0.25  (row-major 2x2 order of the crate's loop)
-#pragma unroll
-        for (int a = 0; a < 2; a++)
-#pragma unroll
-            for (int b = 0; b < 2; b++)
-#pragma unroll
-                for (int c = 0; c < 3; c++)
-                    l1[a][b][c] = (((quad[2 * a][2 * b][c] + quad[2 * a][2 * b + 1][c]) + quad[2 * a + 1][2 * b][c]) +
-                                   quad[2 * a + 1][2 * b + 1][c]) * 0.25f;
         float l2[3];
+        const bool copy = base && !changed;
+        if (copy) {
+            // an unchanged block has the base image's linear scale-2 pixel as well (k_pyramid keeps it in the unused scale-0 area
+            // of the base pyramid buffer): no table lookups, no downscaling
 #pragma unroll
-        for (int c = 0; c < 3; c++) l2[c] = (((l1[0][0][c] + l1[0][1][c]) + l1[1][0][c]) + l1[1][1][c]) * 0.25f;
+            for (int c = 0; c < 3; c++) l2[c] = __ldg(base + c * 4096 + (y0 >> 2) * 64 + (x0 >> 2));
+        } else {
+            float quad[4][4][3];
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int gi = (outw[r] >> (8 * c)) & 255;
+                    quad[r][c][0] = s_lin[gi][0];
+                    quad[r][c][1] = s_lin[gi][1];
+                    quad[r][c][2] = s_lin[gi][2];
+                }
+            // downscale_by_2: ((p00 + p01) + p10) + p11, * 0.25  (row-major 2x2 order of the crate's loop)
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int b = 0; b < 2; b++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++)
+                        l1[a][b][c] = (((quad[2 * a][2 * b][c] + quad[2 * a][2 * b + 1][c]) + quad[2 * a + 1][2 * b][c]) +
+                                       quad[2 * a + 1][2 * b + 1][c]) * 0.25f;
+#pragma unroll
+            for (int c = 0; c < 3; c++) l2[c] = (((l1[0][0][c] + l1[0][1][c]) + l1[1][0][c]) + l1[1][1][c]) * 0.25f;
+        }
         const size_t o1 = 3 * (size_t)scale_off(1) + (size_t)(y0 >> 1) * 128 + (x0 >> 1);   // scale 1: 128 x 128
         const size_t o2 = 3 * (size_t)scale_off(2) + (size_t)(y0 >> 2) * 64 + (x0 >> 2);    // scale 2: 64 x 64
         int slot = -1;
@@ -302,7 +314,7 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) k_assign_pyr(const Img
             slot = atomicAdd(&s_njobs, 5);
             if (slot + 5 > PYR_MAXJOBS) slot = -1;   // queue full: convert in place
         }
-        if (base && !changed) {
+        if (copy) {
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 const size_t oc = o1 + (size_t)c * 128 * 128;

@@ -252,6 +252,11 @@ __global__ void __launch_bounds__(256) k_pyramid(const ImgDev *imgs, const CandE
                 float(*nxt)[256] = linbuf[(L + 1) & 1];
 #pragma unroll
                 for (int c = 0; c < 3; c++) nxt[c][ay * m + ax] = cur[c];
+                // the prepared base assignment also keeps its LINEAR scale-2 plane ([3][64][64]), in the scale-0 area of the buffer,
+                // which candidates never use: k_assign_pyr reads it for the 4x4 blocks a candidate leaves unchanged
+                if (!SRC && from_image == 2 && L == 2)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) rm[c * 4096 + (by * m + ay) * 64 + bx * m + ax] = cur[c];
             }
             __syncthreads();
             if (active) {
