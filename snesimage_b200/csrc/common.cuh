@@ -149,7 +149,7 @@ __device__ __forceinline__ float msun_cbrtf_fast(float x, unsigned *fallbacks = 
     return msun_cbrtf(x);
 #else
     const uint32_t bits = __float_as_uint(x);
-    if (bits - 0x00800000u >= 0x7f000000u) return msun_cbrtf_call(x);   // zero, subnormal, infinite, NaN, negative
+    if (bits - 0x00800000u >= 0x7b000000u) return msun_cbrtf_call(x);   // zero, subnormal, >= 2^120 (the reciprocal of 3x must stay a normal float), infinite, NaN, negative
     const float t0 = __uint_as_float(bits / 3 + 709958130u);
     const float r0 = (t0 * t0) * t0;
     const float t1 = t0 * __fdividef((x + x) + r0, (x + r0) + r0);

@@ -24,8 +24,10 @@ def test_fast_cbrt_is_the_exact_one(ctx):
     bad, fb = ctx.cbrt_selfcheck(2.0 ** -9, 2.0)
     assert bad == 0
     assert 0 < fb < 84e6 * 2e-4            # the fallback exists and is rare (6e-5 expected)
-    bad, fb = ctx.cbrt_selfcheck(0.0, 2.0 ** -120)
-    assert bad == 0
+    # the ends of the line (the fast path stops at 2^120) and negative numbers, which go to the exact function
+    for lo, hi in ((0.0, 2.0 ** -120), (2.0 ** 118, float(np.finfo(np.float32).max)), (-1.0, -2.0)):
+        bad, fb = ctx.cbrt_selfcheck(lo, hi)
+        assert bad == 0
 
 
 @pytest.mark.parametrize("family", ["V", "G", "B", "T"])
