@@ -310,3 +310,34 @@ def test_golden_regression_vectors():
             assert abs(now[k] - gold[k]) <= 1e-9 * max(1.0, abs(gold[k])), k
         else:
             assert now[k] == gold[k], k
+
+
+def test_ciede2000_lightness_lower_bound_of_the_cielab_candidate_kernel():
+    """k_assign_pyr<1> (assign_delta.cuh) decides a pixel without the CIEDE2000 formula when |dL| / 1.75 exceeds the pixel's threshold
+    times 1.001 plus 1e-3.  That is safe iff the f32 distance d satisfies |dL| / 1.75 <= 1.001 d + 1e-3 for every pair the kernel can
+    meet: candidate = a BGR555 colour through as_rgba, pixel = any sRGB8 colour.  Mathematically dE00 >= |dL| / SL with SL <= 1.747
+    (the chroma / hue terms form a positive-semidefinite quadratic because |RT| < 2); here the oracle's f32 evaluation is asked."""
+    rng = np.random.RandomState(11)
+    n = 60000
+    cand5 = rng.randint(0, 32, (n, 3))
+    pix = rng.randint(0, 256, (n, 3))
+    # the corners of the bound: saturated blues and purples (where RT is largest), greys, near-identical and extreme-lightness pairs
+    pix[:4000, 2] = rng.randint(200, 256, 4000)
+    pix[:4000, :2] = rng.randint(0, 60, (4000, 2))
+    cand5[:2000] = np.stack([rng.randint(0, 8, 2000), rng.randint(0, 8, 2000), rng.randint(24, 32, 2000)], axis=1)
+    pix[4000:6000] = np.repeat(rng.randint(0, 256, (2000, 1)), 3, axis=1)
+    cand5[5000:7000] = np.repeat(rng.randint(0, 32, (2000, 1)), 3, axis=1)
+    pix[7000:7100] = 255
+    cand5[7000:7100] = 0
+    pix[7100:7200] = 0
+    cand5[7100:7200] = 31
+    worst = np.inf
+    for c5, p in zip(cand5, pix):
+        c8 = ob.snes_as_rgba(c5.astype(np.uint8))[:3]
+        lc, lp = ob.srgb8_to_lab(*[int(v) for v in c8]), ob.srgb8_to_lab(*[int(v) for v in p])
+        d = ob.ciede2000_f32(lc, lp)                       # argument order of lib.rs:783: (palette colour, target)
+        lb = abs(float(lc[0]) - float(lp[0])) / 1.75
+        assert lb <= 1.001 * d + 1e-3, (c5, p, d, lb)
+        if lb > 1.0:
+            worst = min(worst, d / lb)
+    assert worst >= 1.0     # the bound itself, without the kernel's margin, on every pair with a lightness difference above 1.75
