@@ -105,7 +105,8 @@ int snes_ctx_set_transfer_luts(snes_ctx *ctx, const float *yuvxyb_eotf /* 256 or
 int snes_ctx_set_all_terms(snes_ctx *ctx, int on);
 /* Self-check of the kernels' cube root (yuvxyb's cbrtf = FreeBSD msun s_cbrtf.c, the opsin transfer of linear_rgb_to_xyb): the
  * kernels evaluate it with one f32 and one division-free f64 Halley step and fall back to the restated msun function wherever the
- * f64 result is too close to an f32 rounding boundary for the two to be guaranteed equal (common.cuh: msun_cbrtf_fast).  This runs
+ * f64 result is too close to an f32 rounding boundary for the two to be guaranteed equal, and for inputs outside [2^-126, 2^120)
+ * (common.cuh: msun_cbrtf_fast).  This runs
  * both on every float whose bit pattern lies in [lo_bits, hi_bits) and counts the inputs on which they differ (must be 0) and the
  * inputs that took the fallback. */
 int snes_ctx_cbrt_selfcheck(snes_ctx *ctx, uint32_t lo_bits, uint32_t hi_bits, uint64_t *mismatches, uint64_t *fallbacks);
